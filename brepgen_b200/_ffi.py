@@ -1,0 +1,74 @@
+"""ctypes binding of libbrepgen_b200.so (the C ABI in include/brepgen_b200.h).
+
+The product path has NO fallback: if the shared library is missing or the device is not sm_100, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbrepgen_b200.so")
+
+vp, i32, i64, u64, f32, sz = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float, C.c_size_t
+
+
+class BgNamedTensor(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("data", vp), ("numel", i64)]
+
+
+class BgDenoiserArgs(C.Structure):
+    _fields_ = [("B", i32), ("S", i32), ("E", i32), ("x", vp), ("timesteps", vp), ("n_timesteps", i32),
+                ("surfPos", vp), ("surfZ", vp), ("edgePos", vp), ("mask", vp), ("class_label", vp), ("out", vp)]
+
+
+# name -> (restype, argtypes); every symbol include/brepgen_b200.h declares (tests check the export list against this)
+SIGNATURES = {
+    "bg_version": (i32, []),
+    "bg_last_error": (C.c_char_p, []),
+    "bg_check_device": (i32, []),
+    "bg_denoiser_create": (i32, [i32, i32, C.POINTER(BgNamedTensor), i32, vp, vp, C.POINTER(vp)]),
+    "bg_denoiser_destroy": (None, [vp]),
+    "bg_denoiser_workspace_bytes": (sz, [vp, i32, i32, i32]),
+    "bg_denoiser_forward": (i32, [vp, C.POINTER(BgDenoiserArgs), vp, sz, vp]),
+    "bg_ddpm_step": (i32, [vp, vp, f32, vp, vp, vp, u64, u64, i64, f32, f32, f32, f32, f32, f32, vp]),
+    "bg_pndm_step": (i32, [vp, vp, i64, f32, f32, vp, f32, vp, f32, vp, f32, vp, f32, vp]),
+    "bg_axpby": (i32, [vp, f32, vp, f32, vp, i64, vp]),
+    "bg_op_gemm_f16": (i32, [vp, i32, vp, i32, i32, i32, i32, vp, i32, i32, i32, vp, vp, i32, vp, i32, i32, vp]),
+    "bg_op_attention": (i32, [vp, vp, i32, i32, vp, i32, vp, vp]),
+    "bg_op_layernorm_f16": (i32, [vp, i32, vp, vp, vp, i32, i32, i32, vp]),
+    "bg_op_cast_f16": (i32, [vp, vp, i64, vp]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(brepgen_b200 has no CPU / PyTorch fallback)")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = l
+    return _lib
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        msg = lib().bg_last_error().decode(errors="replace")
+        raise RuntimeError(f"brepgen_b200 {what} failed (status {status}): {msg}")
+
+
+def ptr(t) -> Optional[int]:
+    """device pointer of a torch tensor (or None)"""
+    return None if t is None else t.data_ptr()
+
+
+def current_stream() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,378 @@
+// tcgen05 flash attention for the denoisers' self-attention (12 heads x 64, key-padding mask).
+//
+// Reference semantics: nn.MultiheadAttention inside nn.TransformerEncoderLayer with src_key_padding_mask
+// (/root/reference/network.py:1119-1123, 1193-1197, 1279-1283, 1387-1390): softmax(q k^T / 8 + (-inf on padded keys)) v.
+// Edge stages run ONE sequence of L = faces*edges <= 4000 tokens per sample (network.py:1265-1283), so this is an
+// online-softmax (flash) kernel; the surface stages (L <= 100) use the same kernel with one key block.
+//
+// CTA = NT query tiles of 128 rows for one (sample, head):
+//   warps [0, 4*NT) : softmax warpgroups, one per query tile; thread r owns query row r == TMEM lane r
+//   warp 4*NT       : TMA producer (Q once; K / V 128-key tiles through an ST-deep mbarrier ring)
+//   warp 4*NT+1     : TMEM allocator + MMA issuer (one elected thread)
+// per key block j and tile t:   S_t = Q_t K_j^T            4 x tcgen05.mma M128 N128 K16  (A,B K-major SW128)
+//                               P_t = exp2(c (S_t - m))     softmax WG: TMEM -> regs -> fp16 -> swizzled smem
+//                               PV_t = P_t V_j              8 x tcgen05.mma M128 N64 K16   (B = V, MN-major SW128)
+//                               O_t = (O_t + PV_{j-1}) * alpha   in registers (fp32)
+// MMA issue order  QK(0,j) QK(1,j) PV(0,j-1) PV(1,j-1)  lets softmax of block j overlap the PV of block j-1.
+// Fully padded key blocks are skipped through a per-sample block list (result-preserving: their p is exactly 0).
+// Roofline: tensor-bound; 4*L*L*64 flop per (sample, head).
+#include <math.h>
+
+#include "bg_internal.h"
+#include "ptx.cuh"
+
+namespace bg {
+
+namespace {
+
+constexpr int DH = 64;
+constexpr int NHEAD = 12;
+constexpr int DMODEL = 768;
+constexpr int TILE_BYTES = 128 * DH * 2;   // 16 KB: Q / K / V tile, 128 rows x 128 B
+constexpr int P_BYTES = 128 * 128 * 2;     // 32 KB: two K-major SW128 blocks of 64 keys
+
+template <int NT>
+struct ACfg {
+  static constexpr int ST = (NT == 2) ? 3 : 2;
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_K = NT * TILE_BYTES;
+  static constexpr int OFF_V = OFF_K + ST * TILE_BYTES;
+  static constexpr int OFF_P = OFF_V + ST * TILE_BYTES;
+  static constexpr int OFF_BAR = OFF_P + NT * P_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
+  static constexpr int TMEM_COLS = (NT == 2) ? 512 : 256;
+  static constexpr int THREADS = NT * 128 + 64;
+  static constexpr int TILE_COLS = 192;   // per tile: S at +0 (128 cols), PV at +128 (64 cols)
+};
+
+struct AttnParams {
+  __half* out;
+  int ldo;
+  int B, L, nkb;
+  const uint8_t* key_mask;
+  const int* blk_list;
+  const int* blk_count;
+  float scale_log2;   // log2(e) / sqrt(64)
+};
+
+template <int NT>
+__global__ void __launch_bounds__(ACfg<NT>::THREADS, (NT == 2) ? 1 : 2)
+attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
+  using C = ACfg<NT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = q_full + 1;
+  uint64_t* k_empty = k_full + C::ST;
+  uint64_t* v_full = k_empty + C::ST;
+  uint64_t* v_empty = v_full + C::ST;
+  uint64_t* s_full = v_empty + C::ST;
+  uint64_t* s_free = s_full + NT;
+  uint64_t* p_full = s_free + NT;
+  uint64_t* pv_full = p_full + NT;
+  uint64_t* pv_free = pv_full + NT;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_free + NT);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int qgrp = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int nblk = p.blk_count ? p.blk_count[b] : p.nkb;
+  const int* blist = p.blk_list ? p.blk_list + (size_t)b * p.nkb : nullptr;
+
+  constexpr int PRODUCER_WARP = NT * 4;
+  constexpr int MMA_WARP = NT * 4 + 1;
+
+  if (warp == PRODUCER_WARP && elect_one()) {
+    tma_prefetch_desc(&tmQKV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < C::ST; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
+    for (int t = 0; t < NT; ++t) {
+      mbar_init(&s_full[t], 1);
+      mbar_init(&s_free[t], 128);
+      mbar_init(&p_full[t], 128);
+      mbar_init(&pv_full[t], 1);
+      mbar_init(&pv_free[t], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == MMA_WARP) tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == PRODUCER_WARP) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(q_full, NT * TILE_BYTES);
+      for (int t = 0; t < NT; ++t)
+        tma_load_3d(smem + C::OFF_Q + t * TILE_BYTES, &tmQKV, q_full, h * DH, (qgrp * NT + t) * 128, b);
+      for (int it = 0; it < nblk; ++it) {
+        const int kb = blist ? blist[it] : it;
+        const int s = it % C::ST;
+        const uint32_t par = ((it / C::ST) & 1) ^ 1;
+        mbar_wait(&k_empty[s], par);
+        mbar_arrive_expect_tx(&k_full[s], TILE_BYTES);
+        tma_load_3d(smem + C::OFF_K + s * TILE_BYTES, &tmQKV, &k_full[s], DMODEL + h * DH, kb * 128, b);
+        mbar_wait(&v_empty[s], par);
+        mbar_arrive_expect_tx(&v_full[s], TILE_BYTES);
+        tma_load_3d(smem + C::OFF_V + s * TILE_BYTES, &tmQKV, &v_full[s], 2 * DMODEL + h * DH, kb * 128, b);
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    if (elect_one()) {
+      constexpr uint32_t idesc_qk = make_idesc_f16(128, 128, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_f16(128, DH, 0, 1);   // B (= V) is MN-major
+      mbar_wait(q_full, 0);
+      tc_fence_after();
+      for (int it = 0; it <= nblk; ++it) {
+        if (it < nblk) {
+          const int s = it % C::ST;
+          mbar_wait(&k_full[s], (it / C::ST) & 1);
+          tc_fence_after();
+          const uint32_t k_addr = smem_u32(smem + C::OFF_K + s * TILE_BYTES);
+#pragma unroll
+          for (int t = 0; t < NT; ++t) {
+            mbar_wait(&s_free[t], (it & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t q_addr = smem_u32(smem + C::OFF_Q + t * TILE_BYTES);
+#pragma unroll
+            for (int k = 0; k < DH / 16; ++k)
+              umma_f16_ss(tmem_base + t * C::TILE_COLS, make_sw128_desc(q_addr + k * 32), make_sw128_desc(k_addr + k * 32),
+                          idesc_qk, k > 0 ? 1u : 0u);
+            umma_commit(&s_full[t]);
+          }
+          umma_commit(&k_empty[s]);
+        }
+        if (it > 0) {
+          const int i = it - 1;
+          const int s = i % C::ST;
+          mbar_wait(&v_full[s], (i / C::ST) & 1);
+          const uint32_t v_addr = smem_u32(smem + C::OFF_V + s * TILE_BYTES);
+#pragma unroll
+          for (int t = 0; t < NT; ++t) {
+            mbar_wait(&p_full[t], i & 1);
+            mbar_wait(&pv_free[t], (i & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t p_addr = smem_u32(smem + C::OFF_P + t * P_BYTES);
+#pragma unroll
+            for (int k = 0; k < 128 / 16; ++k)
+              umma_f16_ss(tmem_base + t * C::TILE_COLS + 128,
+                          make_sw128_desc(p_addr + (k >> 2) * (P_BYTES / 2) + (k & 3) * 32),
+                          make_sw128_desc(v_addr + k * 2048), idesc_pv, k > 0 ? 1u : 0u);
+            umma_commit(&pv_full[t]);
+          }
+          umma_commit(&v_empty[s]);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax warpgroup for query tile t
+    const int t = warp >> 2;
+    const int r = threadIdx.x & 127;                       // query row in tile == TMEM lane
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t s_tmem = tmem_base + lane_base + t * C::TILE_COLS;
+    const uint32_t pv_tmem = s_tmem + 128;
+    uint8_t* sP = smem + C::OFF_P + t * P_BYTES;
+    const float c = p.scale_log2;
+
+    float m = -INFINITY, l = 0.f;
+    float o[DH];
+#pragma unroll
+    for (int i = 0; i < DH; ++i) o[i] = 0.f;
+
+    for (int it = 0; it < nblk; ++it) {
+      const int kb = blist ? blist[it] : it;
+      // invalid-key bit masks for the 4 x 32 keys of this block (padded key or beyond L)
+      uint32_t inval[4];
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        const int key = kb * 128 + cc * 32 + lane;
+        bool bad = key >= p.L;
+        if (!bad && p.key_mask) bad = p.key_mask[(size_t)b * p.L + key] != 0;
+        inval[cc] = __ballot_sync(0xffffffffu, bad);
+      }
+
+      mbar_wait(&s_full[t], it & 1);
+      tc_fence_after();
+
+      // pass 1: row max
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t rr[32];
+        tmem_ld_32x32b_x32(s_tmem + cc * 32, rr);
+        tmem_ld_wait();
+        const uint32_t w = inval[cc];
+        if (w == 0) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(rr[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, ((w >> i) & 1u) ? -INFINITY : __uint_as_float(rr[i]));
+        }
+      }
+      const float m_new = fmaxf(m, mx);
+      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+      const float alpha = ex2((m - m_use) * c);            // m = -inf -> 0
+      const float mc = m_use * c;
+
+      // fold in PV of the previous block (also guarantees the PV MMA no longer reads sP)
+      if (it > 0) {
+        mbar_wait(&pv_full[t], (it - 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t rr[32];
+          tmem_ld_32x32b_x32(pv_tmem + hh * 32, rr);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[hh * 32 + i] = (o[hh * 32 + i] + __uint_as_float(rr[i])) * alpha;
+        }
+        tc_fence_before();
+        mbar_arrive(&pv_free[t]);
+      }
+
+      // pass 2: p = exp2(c s - c m), row sum, fp16 P into the K-major SW128 layout
+      float rowsum = 0.f;
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t rr[32];
+        tmem_ld_32x32b_x32(s_tmem + cc * 32, rr);
+        tmem_ld_wait();
+        const uint32_t w = inval[cc];
+        float pr[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float e = ex2(fmaf(__uint_as_float(rr[i]), c, -mc));
+          if (w != 0 && ((w >> i) & 1u)) e = 0.f;
+          pr[i] = e;
+          rowsum += e;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int j8 = cc * 4 + q;                       // 16-byte chunk index along the 128 keys
+          __half2 h0 = __floats2half2_rn(pr[8 * q], pr[8 * q + 1]);
+          __half2 h1 = __floats2half2_rn(pr[8 * q + 2], pr[8 * q + 3]);
+          __half2 h2 = __floats2half2_rn(pr[8 * q + 4], pr[8 * q + 5]);
+          __half2 h3 = __floats2half2_rn(pr[8 * q + 6], pr[8 * q + 7]);
+          uint4 u;
+          u.x = *reinterpret_cast<uint32_t*>(&h0);
+          u.y = *reinterpret_cast<uint32_t*>(&h1);
+          u.z = *reinterpret_cast<uint32_t*>(&h2);
+          u.w = *reinterpret_cast<uint32_t*>(&h3);
+          uint8_t* dst = sP + (j8 >> 3) * (P_BYTES / 2) + r * 128 + (((j8 & 7) ^ (r & 7)) << 4);
+          *reinterpret_cast<uint4*>(dst) = u;
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&s_free[t]);          // S_t may be overwritten by QK of the next block
+      fence_proxy_async_smem();         // generic-proxy writes of P -> visible to the tensor core (async proxy)
+      mbar_arrive(&p_full[t]);
+      l = l * alpha + rowsum;
+      m = m_new;
+    }
+
+    if (nblk > 0) {
+      mbar_wait(&pv_full[t], (nblk - 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t rr[32];
+        tmem_ld_32x32b_x32(pv_tmem + hh * 32, rr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[hh * 32 + i] += __uint_as_float(rr[i]);
+      }
+    }
+    const int row = (qgrp * NT + t) * 128 + r;
+    if (row < p.L) {
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+      uint4* dst = reinterpret_cast<uint4*>(p.out + ((size_t)b * p.L + row) * p.ldo + h * DH);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        __half2 h0 = __floats2half2_rn(o[8 * q] * inv, o[8 * q + 1] * inv);
+        __half2 h1 = __floats2half2_rn(o[8 * q + 2] * inv, o[8 * q + 3] * inv);
+        __half2 h2 = __floats2half2_rn(o[8 * q + 4] * inv, o[8 * q + 5] * inv);
+        __half2 h3 = __floats2half2_rn(o[8 * q + 6] * inv, o[8 * q + 7] * inv);
+        uint4 u;
+        u.x = *reinterpret_cast<uint32_t*>(&h0);
+        u.y = *reinterpret_cast<uint32_t*>(&h1);
+        u.z = *reinterpret_cast<uint32_t*>(&h2);
+        u.w = *reinterpret_cast<uint32_t*>(&h3);
+        dst[q] = u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) tmem_dealloc<C::TMEM_COLS>(tmem_base);
+}
+
+// one CTA per sample: which 128-key blocks hold at least one valid key
+__global__ void block_list_kernel(const uint8_t* __restrict__ key_mask, int L, int nkb, int* __restrict__ blk_list,
+                                  int* __restrict__ blk_count) {
+  extern __shared__ int flags[];
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  for (int kb = warp; kb < nkb; kb += nwarp) {
+    bool any = false;
+    for (int i = lane; i < 128; i += 32) {
+      const int key = kb * 128 + i;
+      if (key < L && key_mask[(size_t)b * L + key] == 0) any = true;
+    }
+    any = __any_sync(0xffffffffu, any);
+    if (lane == 0) flags[kb] = any ? 1 : 0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int n = 0;
+    for (int kb = 0; kb < nkb; ++kb)
+      if (flags[kb]) blk_list[(size_t)b * nkb + n++] = kb;
+    blk_count[b] = n;
+  }
+}
+
+template <int NT>
+int launch_nt(cudaStream_t st, const CUtensorMap& tm, const AttnParams& p) {
+  using C = ACfg<NT>;
+  static bool configured = false;
+  if (!configured) {
+    BG_CUDA(cudaFuncSetAttribute(attn_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    configured = true;
+  }
+  const int nq = (p.L + 127) / 128;
+  dim3 grid((nq + NT - 1) / NT, NHEAD, p.B);
+  attn_kernel<NT><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(tm, p);
+  return check_cuda(cudaGetLastError(), "attn_kernel launch");
+}
+
+}  // namespace
+
+int launch_attention(cudaStream_t st, const AttnArgs& a) {
+  BG_REQUIRE(a.qkv && a.out && a.B > 0 && a.L > 0, "attention: bad arguments");
+  BG_REQUIRE(a.ldo % 8 == 0, "attention: output pitch must be a multiple of 8");
+  BG_REQUIRE((a.blk_list == nullptr) == (a.blk_count == nullptr), "attention: blk_list and blk_count go together");
+  CUtensorMap tm;
+  BG_TRY(make_tmap_3d_f16(&tm, a.qkv, (uint64_t)a.B, (uint64_t)a.L, 3 * DMODEL, 3 * DMODEL, 128));
+  AttnParams p;
+  p.out = a.out; p.ldo = a.ldo; p.B = a.B; p.L = a.L; p.nkb = (a.L + 127) / 128;
+  p.key_mask = a.key_mask; p.blk_list = a.blk_list; p.blk_count = a.blk_count;
+  p.scale_log2 = 1.4426950408889634f / 8.0f;
+  return (a.L > 128) ? launch_nt<2>(st, tm, p) : launch_nt<1>(st, tm, p);
+}
+
+int launch_build_block_list(cudaStream_t st, const uint8_t* key_mask, int B, int L, int* blk_list, int* blk_count) {
+  BG_REQUIRE(key_mask && blk_list && blk_count && B > 0 && L > 0, "block list: bad arguments");
+  const int nkb = (L + 127) / 128;
+  block_list_kernel<<<B, 128, nkb * sizeof(int), st>>>(key_mask, L, nkb, blk_list, blk_count);
+  return check_cuda(cudaGetLastError(), "block_list_kernel launch");
+}
+
+}  // namespace bg

@@ -1,0 +1,97 @@
+// Internal (C++) interface between the translation units of libbrepgen_b200.so. Not part of the C ABI.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include <string>
+
+namespace bg {
+
+// ---- error plumbing (no C++ exception crosses the C ABI) ----
+enum Status : int {
+  BG_OK = 0,
+  BG_ERR_BAD_ARG = -1,
+  BG_ERR_UNSUPPORTED_ARCH = -2,
+  BG_ERR_CUDA = -3,
+  BG_ERR_WORKSPACE = -4,
+  BG_ERR_MISSING_WEIGHT = -5,
+};
+int set_error(int code, const std::string& msg);
+int check_cuda(cudaError_t e, const char* what);
+#define BG_CUDA(x)                                              \
+  do {                                                          \
+    int _s = ::bg::check_cuda((x), #x);                         \
+    if (_s != 0) return _s;                                     \
+  } while (0)
+#define BG_TRY(x)                    \
+  do {                               \
+    int _s = (x);                    \
+    if (_s != 0) return _s;          \
+  } while (0)
+#define BG_REQUIRE(cond, msg)                                                           \
+  do {                                                                                  \
+    if (!(cond)) return ::bg::set_error(::bg::BG_ERR_BAD_ARG, std::string(msg) + " [" #cond "]"); \
+  } while (0)
+
+int num_sms();   // of the current device (cached)
+
+// ---- TMA descriptor creation (driver entry point resolved at run time; no link dependency on libcuda) ----
+// 2-D fp16 row-major [rows][cols] with row pitch ld (elements); box = {box_cols(=64), box_rows}; SWIZZLE_128B.
+int make_tmap_2d_f16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                     uint32_t box_cols = 64);
+// 3-D fp16 [batch][rows][cols] (row pitch ld, batch pitch = rows*ld); box = {64, box_rows, 1}; SWIZZLE_128B.
+int make_tmap_3d_f16(CUtensorMap* out, const void* base, uint64_t batch, uint64_t rows, uint64_t cols, uint64_t ld,
+                     uint32_t box_rows);
+
+// ---- tcgen05 GEMM:  out[M,N] = epilogue( A[M,K] (fp16, pitch lda) * W[N,K]^T (fp16, pitch ldw) ) ----
+struct GemmEpilogue {
+  void* out = nullptr;           // fp16 or fp32, pitch ldo (elements)
+  int ldo = 0;
+  int out_f16 = 1;
+  int relu = 0;
+  const float* bias = nullptr;   // [N]
+  const float* resid = nullptr;  // fp32 [M, ldr] added (may alias out when out is fp32)
+  int ldr = 0;
+  const float* rowvec = nullptr; // fp32 [(M / rows_per_vec), ldv]: row r adds rowvec[r / rows_per_vec]
+  int rows_per_vec = 1;
+  int ldv = 0;
+};
+int launch_gemm_f16(cudaStream_t st, const __half* A, int lda, const __half* W, int ldw, int M, int N, int K,
+                    const GemmEpilogue& ep);
+
+// ---- tcgen05 flash attention over packed QKV [B*L, 2304] fp16 (q | k | v, head h at +64h) ----
+struct AttnArgs {
+  const __half* qkv = nullptr;      // [B*L, 3*768]
+  __half* out = nullptr;            // [B*L, ldo] head h at column 64h
+  int ldo = 768;
+  int B = 0, L = 0;
+  const uint8_t* key_mask = nullptr;   // [B, L] nonzero = padded key (ignored), or null
+  const int* blk_list = nullptr;       // [B, nkb] key blocks (of 128) with >=1 valid key, or null = all
+  const int* blk_count = nullptr;      // [B]
+};
+int launch_attention(cudaStream_t st, const AttnArgs& a);
+// builds blk_list/blk_count from key_mask ([B,L]); nkb = ceil(L/128)
+int launch_build_block_list(cudaStream_t st, const uint8_t* key_mask, int B, int L, int* blk_list, int* blk_count);
+
+// ---- CUDA-core kernels (HBM-bound glue) ----
+// y[row, 0:768] (fp16, pitch ldy) = act(LayerNorm(x[row, 0:768]) * g + b); act: 0 none, 1 SiLU.   eps = 1e-5
+int launch_layernorm_f16(cudaStream_t st, const float* x, int ldx, const float* g, const float* b, __half* y, int ldy,
+                         int rows, int act);
+// y (fp16, pitch ldy) = SiLU(LayerNorm(x[row,0:d_in] * W0^T + b0)); W0t is [d_in][768] fp32 (transposed Linear weight)
+int launch_embed_in(cudaStream_t st, const float* x, int ldx, int d_in, const float* W0t, const float* b0, const float* g,
+                    const float* b, __half* y, int ldy, int rows);
+// out[row, 0:d_out] (fp32) = h[row, 0:768] (fp16) * W^T + bias;  W [d_out][768] fp32, d_out <= 64
+int launch_head_out(cudaStream_t st, const __half* h, int ldh, const float* W, const float* bias, float* out, int d_out,
+                    int rows);
+// cond[b, :] = time_table[t_b, :] + (class_table ? class_table[label_b, :] : 0);  t: int64 [n_t] (n_t = 1 or B)
+int launch_cond(cudaStream_t st, const float* time_table, const int64_t* t, int n_t, const float* class_table,
+                const int64_t* label, float* cond, int B);
+// sincos rows for t = 0..n-1:  out[t, :] = [cos(t f) | sin(t f)], f_i = exp(-ln(1e4) i / 384)   (fp32, 768 wide)
+int launch_sincos_table(cudaStream_t st, float* out, int n);
+int launch_cast_f32_to_f16(cudaStream_t st, const float* x, __half* y, size_t n);
+int launch_mask_expand(cudaStream_t st, const uint8_t* face_mask, uint8_t* edge_mask, int BS, int E);
+
+}  // namespace bg

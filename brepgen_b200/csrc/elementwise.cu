@@ -1,0 +1,253 @@
+// CUDA-core kernels around the tensor-core contractions: LayerNorm -> fp16, the tiny-K / tiny-N ends of the embed
+// MLPs, conditioning vectors, casts.  All HBM-bound: coalesced 16-byte accesses, one warp per token row.
+//
+// Reference: the Linear -> LayerNorm -> SiLU -> Linear embed MLPs and norm1/norm2/final norm of the encoder,
+// /root/reference/network.py:1080-1099 (and the analogous blocks of the other three nets); sincos_embedding :1043-1063.
+#include <math.h>
+
+#include "bg_internal.h"
+
+namespace bg {
+
+namespace {
+
+constexpr int D = 768;
+constexpr float LN_EPS = 1e-5f;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float silu(float x) { return x / (1.f + __expf(-x)); }
+
+// v[24] holds row elements {lane*4 + 128*j + i}; normalise in place (two-pass, fp32)
+__device__ __forceinline__ void ln_row(float (&v)[24], const float* __restrict__ g, const float* __restrict__ b, int lane,
+                                       int act) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 24; ++i) s += v[i];
+  const float mean = warp_sum(s) * (1.f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 24; ++i) {
+    const float d = v[i] - mean;
+    q += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.f / D) + LN_EPS);
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    const float4 gg = __ldg(reinterpret_cast<const float4*>(g + lane * 4 + 128 * j));
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(b + lane * 4 + 128 * j));
+    float y0 = (v[4 * j] - mean) * rstd * gg.x + bb.x;
+    float y1 = (v[4 * j + 1] - mean) * rstd * gg.y + bb.y;
+    float y2 = (v[4 * j + 2] - mean) * rstd * gg.z + bb.z;
+    float y3 = (v[4 * j + 3] - mean) * rstd * gg.w + bb.w;
+    if (act == 1) { y0 = silu(y0); y1 = silu(y1); y2 = silu(y2); y3 = silu(y3); }
+    v[4 * j] = y0; v[4 * j + 1] = y1; v[4 * j + 2] = y2; v[4 * j + 3] = y3;
+  }
+}
+
+__device__ __forceinline__ void store_row_f16(const float (&v)[24], __half* y, int lane) {
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    __half2 h0 = __floats2half2_rn(v[4 * j], v[4 * j + 1]);
+    __half2 h1 = __floats2half2_rn(v[4 * j + 2], v[4 * j + 3]);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&h0);
+    u.y = *reinterpret_cast<uint32_t*>(&h1);
+    *reinterpret_cast<uint2*>(y + lane * 4 + 128 * j) = u;
+  }
+}
+
+__global__ void __launch_bounds__(256) layernorm_f16_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ g,
+                                                            const float* __restrict__ b, __half* __restrict__ y, int ldy,
+                                                            int rows, int act) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
+    const float* xr = x + (size_t)row * ldx;
+    float v[24];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      const float4 t = *reinterpret_cast<const float4*>(xr + lane * 4 + 128 * j);
+      v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+    }
+    ln_row(v, g, b, lane, act);
+    store_row_f16(v, y + (size_t)row * ldy, lane);
+  }
+}
+
+// Linear(d_in -> 768) + LayerNorm + SiLU -> fp16.  W0t: [d_in][768].
+__global__ void __launch_bounds__(256) embed_in_kernel(const float* __restrict__ x, int ldx, int d_in,
+                                                       const float* __restrict__ W0t, const float* __restrict__ b0,
+                                                       const float* __restrict__ g, const float* __restrict__ b,
+                                                       __half* __restrict__ y, int ldy, int rows) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
+    const float* xr = x + (size_t)row * ldx;
+    float v[24];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(b0 + lane * 4 + 128 * j));
+      v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+    }
+    for (int k = 0; k < d_in; ++k) {
+      const float xk = __ldg(xr + k);
+      const float* wr = W0t + (size_t)k * D;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(wr + lane * 4 + 128 * j));
+        v[4 * j] = fmaf(xk, t.x, v[4 * j]);
+        v[4 * j + 1] = fmaf(xk, t.y, v[4 * j + 1]);
+        v[4 * j + 2] = fmaf(xk, t.z, v[4 * j + 2]);
+        v[4 * j + 3] = fmaf(xk, t.w, v[4 * j + 3]);
+      }
+    }
+    ln_row(v, g, b, lane, 1);
+    store_row_f16(v, y + (size_t)row * ldy, lane);
+  }
+}
+
+// out[row, o] = bias[o] + sum_k h[row,k] W[o,k];  warp per row, W (fp32 [d_out][768]) staged in shared memory
+__global__ void __launch_bounds__(256) head_out_kernel(const __half* __restrict__ h, int ldh, const float* __restrict__ W,
+                                                       const float* __restrict__ bias, float* __restrict__ out, int d_out,
+                                                       int rows) {
+  extern __shared__ float sW[];   // [d_out][768]
+  for (int i = threadIdx.x; i < d_out * D / 4; i += blockDim.x)
+    reinterpret_cast<float4*>(sW)[i] = __ldg(reinterpret_cast<const float4*>(W) + i);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
+    const __half* hr = h + (size_t)row * ldh;
+    float v[24];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      const uint2 u = *reinterpret_cast<const uint2*>(hr + lane * 4 + 128 * j);
+      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+      const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+      v[4 * j] = a.x; v[4 * j + 1] = a.y; v[4 * j + 2] = c.x; v[4 * j + 3] = c.y;
+    }
+    float mine = 0.f;
+    for (int o = 0; o < d_out; ++o) {
+      const float* wr = sW + o * D;
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const float4 t = *reinterpret_cast<const float4*>(wr + lane * 4 + 128 * j);
+        acc = fmaf(v[4 * j], t.x, acc);
+        acc = fmaf(v[4 * j + 1], t.y, acc);
+        acc = fmaf(v[4 * j + 2], t.z, acc);
+        acc = fmaf(v[4 * j + 3], t.w, acc);
+      }
+      acc = warp_sum(acc);
+      if ((o & 31) == lane) mine = acc + __ldg(bias + o);
+      if ((o & 31) == 31 || o == d_out - 1) {
+        const int o0 = o & ~31;
+        if (o0 + lane <= o) out[(size_t)row * d_out + o0 + lane] = mine;
+      }
+    }
+  }
+}
+
+__global__ void cond_kernel(const float* __restrict__ time_table, const int64_t* __restrict__ t, int n_t,
+                            const float* __restrict__ class_table, const int64_t* __restrict__ label,
+                            float* __restrict__ cond, int B) {
+  const int b = blockIdx.x;
+  long long tt = t[n_t == 1 ? 0 : b];
+  tt = tt < 0 ? 0 : (tt > 999 ? 999 : tt);
+  const float* tr = time_table + (size_t)tt * D;
+  const float* cr = class_table ? class_table + (size_t)label[b] * D : nullptr;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) cond[(size_t)b * D + i] = tr[i] + (cr ? cr[i] : 0.f);
+}
+
+__global__ void sincos_table_kernel(float* __restrict__ out, int n) {
+  const int t = blockIdx.x;
+  if (t >= n) return;
+  for (int i = threadIdx.x; i < D / 2; i += blockDim.x) {
+    // fp32 like the reference: freqs = exp(-ln(1e4) * i / 384); args = float(t) * freqs
+    const float f = expf(-9.210340371976184f * (float)i / 384.f);
+    const float a = (float)t * f;
+    out[(size_t)t * D + i] = cosf(a);
+    out[(size_t)t * D + D / 2 + i] = sinf(a);
+  }
+}
+
+__global__ void cast_kernel(const float* __restrict__ x, __half* __restrict__ y, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) y[i] = __float2half_rn(x[i]);
+}
+
+__global__ void mask_expand_kernel(const uint8_t* __restrict__ face_mask, uint8_t* __restrict__ edge_mask, int BS, int E) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < BS * E) edge_mask[i] = face_mask[i / E];
+}
+
+inline int row_grid(int rows, int wpb) {
+  const int want = (rows + wpb - 1) / wpb;
+  const int cap = num_sms() * 8;
+  return want < cap ? (want > 0 ? want : 1) : cap;
+}
+
+}  // namespace
+
+int launch_layernorm_f16(cudaStream_t st, const float* x, int ldx, const float* g, const float* b, __half* y, int ldy,
+                         int rows, int act) {
+  BG_REQUIRE(rows > 0 && ldx % 4 == 0 && ldy % 4 == 0, "layernorm: bad shape");
+  layernorm_f16_kernel<<<row_grid(rows, 8), 256, 0, st>>>(x, ldx, g, b, y, ldy, rows, act);
+  return check_cuda(cudaGetLastError(), "layernorm_f16_kernel launch");
+}
+
+int launch_embed_in(cudaStream_t st, const float* x, int ldx, int d_in, const float* W0t, const float* b0, const float* g,
+                    const float* b, __half* y, int ldy, int rows) {
+  BG_REQUIRE(rows > 0 && d_in > 0 && ldy % 4 == 0, "embed_in: bad shape");
+  embed_in_kernel<<<row_grid(rows, 8), 256, 0, st>>>(x, ldx, d_in, W0t, b0, g, b, y, ldy, rows);
+  return check_cuda(cudaGetLastError(), "embed_in_kernel launch");
+}
+
+int launch_head_out(cudaStream_t st, const __half* h, int ldh, const float* W, const float* bias, float* out, int d_out,
+                    int rows) {
+  BG_REQUIRE(rows > 0 && d_out > 0 && d_out <= 64 && ldh % 4 == 0, "head_out: bad shape");
+  const int smem = d_out * D * 4;
+  static int configured_for = 0;
+  if (smem > 48 * 1024 && configured_for < smem) {
+    BG_CUDA(cudaFuncSetAttribute(head_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * D * 4));
+    configured_for = 64 * D * 4;
+  }
+  const int want = (rows + 7) / 8;
+  const int cap = num_sms() * 2;
+  head_out_kernel<<<want < cap ? want : cap, 256, smem, st>>>(h, ldh, W, bias, out, d_out, rows);
+  return check_cuda(cudaGetLastError(), "head_out_kernel launch");
+}
+
+int launch_cond(cudaStream_t st, const float* time_table, const int64_t* t, int n_t, const float* class_table,
+                const int64_t* label, float* cond, int B) {
+  BG_REQUIRE(B > 0 && (n_t == 1 || n_t == B), "cond: timesteps must have 1 or B entries");
+  BG_REQUIRE(class_table == nullptr || label != nullptr, "cond: class table without labels");
+  cond_kernel<<<B, 256, 0, st>>>(time_table, t, n_t, class_table, label, cond, B);
+  return check_cuda(cudaGetLastError(), "cond_kernel launch");
+}
+
+int launch_sincos_table(cudaStream_t st, float* out, int n) {
+  sincos_table_kernel<<<n, 128, 0, st>>>(out, n);
+  return check_cuda(cudaGetLastError(), "sincos_table_kernel launch");
+}
+
+int launch_cast_f32_to_f16(cudaStream_t st, const float* x, __half* y, size_t n) {
+  if (n == 0) return BG_OK;
+  size_t blocks = (n + 255) / 256;
+  if (blocks > (size_t)num_sms() * 16) blocks = (size_t)num_sms() * 16;
+  cast_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, y, n);
+  return check_cuda(cudaGetLastError(), "cast_kernel launch");
+}
+
+int launch_mask_expand(cudaStream_t st, const uint8_t* face_mask, uint8_t* edge_mask, int BS, int E) {
+  const int n = BS * E;
+  mask_expand_kernel<<<(n + 255) / 256, 256, 0, st>>>(face_mask, edge_mask, BS, E);
+  return check_cuda(cudaGetLastError(), "mask_expand_kernel launch");
+}
+
+}  // namespace bg

@@ -1,0 +1,260 @@
+// tcgen05 GEMM for sm_100a:  out[M,N] = epi( A[M,K] * W[N,K]^T ),  fp16 operands, fp32 accumulation in TMEM.
+//
+// This is the only dense linear contraction of the denoisers (reference: torch F.linear inside
+// nn.TransformerEncoderLayer / the embed MLPs, /root/reference/network.py:1076-1099) and of the VAE convs
+// (after im2col).  nn.Linear stores W as [N][K] row-major == K-major B operand, so weights are used as packed.
+//
+// Structure (one persistent CTA per SM, 256 threads):
+//   warp 0  : TMA producer  (A tile 128x64, W tile BNx64, SWIZZLE_128B, STAGES-deep mbarrier ring)
+//   warp 1  : MMA issuer    (one elected thread: 4 x tcgen05.mma.kind::f16 M128 N=BN K16 per 64-wide k-block)
+//   warp 2  : TMEM allocator (2 x BN fp32 columns: accumulator double buffer -> epilogue overlaps next tile)
+//   warps 4-7: epilogue     (tcgen05.ld 32x32b, bias / row-vector / residual / ReLU, fp16 or fp32 store)
+// Roofline: tensor-bound; 2*M*N*K flop per launch.
+#include "bg_internal.h"
+#include "ptx.cuh"
+
+namespace bg {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+
+template <int BN>
+struct Cfg {
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual 1 KB alignment
+};
+
+struct GemmParams {
+  int M, N, K;
+  void* out;
+  int ldo;
+  int out_f16;
+  int relu;
+  const float* bias;
+  const float* resid;
+  int ldr;
+  const float* rowvec;
+  int rows_per_vec;
+  int ldv;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1)
+gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* empty = full + C::STAGES;
+  uint64_t* tfull = empty + C::STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_m = (p.M + BM - 1) / BM;
+  const int num_n = p.N / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_k = p.K / BK;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / num_n, n_blk = tile % num_n;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * C::STAGE_BYTES;
+          uint8_t* sB = sA + C::A_BYTES;
+          mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
+          tma_load_2d(sA, &tmA, &full[stage], kb * BK, m_blk * BM);
+          tma_load_2d(sB, &tmB, &full[stage], kb * BK, n_blk * BN);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_f16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t accphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], accphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + C::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            umma_f16_ss(d_tmem, make_sw128_desc(a_addr + k * 32), make_sw128_desc(b_addr + k * 32), idesc,
+                        (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[acc]);
+        acc ^= 1;
+        if (acc == 0) accphase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    const int ew = warp - 4;
+    const int row_in_tile = ew * 32 + lane;
+    int acc = 0;
+    uint32_t accphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      mbar_wait(&tfull[acc], accphase);
+      tc_fence_after();
+      const int row = m_blk * BM + row_in_tile;
+      const bool row_ok = row < p.M;
+      const float* vec = p.rowvec ? p.rowvec + (size_t)(row_ok ? row / p.rows_per_vec : 0) * p.ldv : nullptr;
+      const float* res = p.resid ? p.resid + (size_t)(row_ok ? row : 0) * p.ldr : nullptr;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN + c * 32, r);
+        tmem_ld_wait();
+        if (row_ok) {
+          const int col0 = n_blk * BN + c * 32;
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          if (p.bias) {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float4 t = __ldg(bp + i);
+              v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+            }
+          }
+          if (vec) {
+            const float4* vp = reinterpret_cast<const float4*>(vec + col0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float4 t = __ldg(vp + i);
+              v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+            }
+          }
+          if (res) {
+            const float4* rp = reinterpret_cast<const float4*>(res + col0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float4 t = rp[i];
+              v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+          if (p.out_f16) {
+            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + (size_t)row * p.ldo + col0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              __half2 h0 = __floats2half2_rn(v[8 * i], v[8 * i + 1]);
+              __half2 h1 = __floats2half2_rn(v[8 * i + 2], v[8 * i + 3]);
+              __half2 h2 = __floats2half2_rn(v[8 * i + 4], v[8 * i + 5]);
+              __half2 h3 = __floats2half2_rn(v[8 * i + 6], v[8 * i + 7]);
+              uint4 u;
+              u.x = *reinterpret_cast<uint32_t*>(&h0);
+              u.y = *reinterpret_cast<uint32_t*>(&h1);
+              u.z = *reinterpret_cast<uint32_t*>(&h2);
+              u.w = *reinterpret_cast<uint32_t*>(&h3);
+              op[i] = u;
+            }
+          } else {
+            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)row * p.ldo + col0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) accphase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<C::TMEM_COLS>(tmem_base);
+}
+
+template <int BN>
+int launch_bn(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p) {
+  using C = Cfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    BG_CUDA(cudaFuncSetAttribute(gemm_f16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    configured = true;
+  }
+  const int num_tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
+  const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+  gemm_f16_kernel<BN><<<grid, 256, C::SMEM_BYTES, st>>>(tmA, tmB, p);
+  return check_cuda(cudaGetLastError(), "gemm_f16_kernel launch");
+}
+
+}  // namespace
+
+int launch_gemm_f16(cudaStream_t st, const __half* A, int lda, const __half* W, int ldw, int M, int N, int K,
+                    const GemmEpilogue& ep) {
+  BG_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem");
+  BG_REQUIRE(K % BK == 0, "gemm: K must be a multiple of 64");
+  BG_REQUIRE(N % 128 == 0, "gemm: N must be a multiple of 128");
+  BG_REQUIRE(lda % 8 == 0 && ldw % 8 == 0, "gemm: operand pitch must be a multiple of 8 elements (16 B)");
+  BG_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0,
+             "gemm: operands must be 16-byte aligned");
+  BG_REQUIRE(ep.out != nullptr && ep.ldo % 8 == 0, "gemm: output pitch must be a multiple of 8");
+  BG_REQUIRE((reinterpret_cast<uintptr_t>(ep.out) & 15) == 0, "gemm: output must be 16-byte aligned");
+  BG_REQUIRE(ep.resid == nullptr || (ep.ldr % 4 == 0 && !ep.out_f16 ? true : ep.ldr % 4 == 0), "gemm: resid pitch");
+  BG_REQUIRE(ep.rowvec == nullptr || (ep.rows_per_vec > 0 && ep.ldv % 4 == 0), "gemm: rowvec");
+  const int bn = (N % 256 == 0) ? 256 : 128;
+  CUtensorMap tmA, tmB;
+  BG_TRY(make_tmap_2d_f16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM));
+  BG_TRY(make_tmap_2d_f16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)bn));
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.out = ep.out; p.ldo = ep.ldo; p.out_f16 = ep.out_f16; p.relu = ep.relu;
+  p.bias = ep.bias; p.resid = ep.resid; p.ldr = ep.ldr;
+  p.rowvec = ep.rowvec; p.rows_per_vec = ep.rows_per_vec; p.ldv = ep.ldv;
+  return bn == 256 ? launch_bn<256>(st, tmA, tmB, p) : launch_bn<128>(st, tmA, tmB, p);
+}
+
+}  // namespace bg

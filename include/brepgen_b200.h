@@ -1,0 +1,114 @@
+/* brepgen_b200 -- C ABI of the B200-native BrepGen sampling path (libbrepgen_b200.so).
+ *
+ * The reference (samxuxiang/BrepGen) is pure Python and has NO FFI of its own: its boundary for this path is the
+ * Python class surface  SurfPosNet/SurfZNet/EdgePosNet/EdgeZNet.forward (network.py:1107,1176,1257,1357),
+ * AutoencoderKLFastDecode / AutoencoderKL1DFastDecode .forward (network.py:1013,846) and the diffusers
+ * DDPMScheduler/PNDMScheduler .step used by sample.py:120-299.  brepgen_b200/{models,vae,schedulers}.py mirror that
+ * surface and call the entry points below through ctypes (INTEGRATION.md shows the binding a maintainer adds).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless stated otherwise; fp32 = float, masks = 1 byte
+ *     per element (torch.bool), timesteps / labels = int64.
+ *   - every call is stream-ordered on `stream` (a cudaStream_t passed as void*); no hidden device synchronisation,
+ *     so the calls can be captured into CUDA graphs.
+ *   - return value: 0 on success, negative BgStatus otherwise; bg_last_error() gives the message (thread-local).
+ *   - no C++ exception crosses this boundary.
+ */
+#ifndef BREPGEN_B200_H_
+#define BREPGEN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  BG_STATUS_OK = 0,
+  BG_STATUS_BAD_ARG = -1,
+  BG_STATUS_UNSUPPORTED_ARCH = -2,   /* not an sm_100 device */
+  BG_STATUS_CUDA = -3,
+  BG_STATUS_WORKSPACE = -4,          /* workspace too small */
+  BG_STATUS_MISSING_WEIGHT = -5
+} BgStatus;
+
+int bg_version(void);
+const char* bg_last_error(void);
+/* 0 if the current device is sm_100; BG_STATUS_UNSUPPORTED_ARCH otherwise */
+int bg_check_device(void);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Denoisers.  Replaces  <Net>(use_cf).load_state_dict(...).to(device).eval()  +  <Net>.forward(...)
+ *   kind 0 SurfPosNet  network.py:1066-1126      kind 1 SurfZNet   network.py:1129-1200
+ *   kind 2 EdgePosNet  network.py:1203-1286      kind 3 EdgeZNet   network.py:1289-1393
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct BgDenoiser BgDenoiser;
+
+typedef struct {
+  const char* name;      /* state-dict key, e.g. "net.layers.0.self_attn.in_proj_weight" */
+  const float* data;     /* device fp32, contiguous */
+  int64_t numel;
+} BgNamedTensor;
+
+/* Packs the checkpoint (fp16 copies of the GEMM weights, fp32 norms/biases, the 1000-row time-embedding table).
+ * `sincos` may be NULL (table built on device) or a device fp32 [1000][768] copy of network.py:1043 sincos_embedding
+ * for t = 0..999.  The weights may be freed after the call returns AND `stream` has been synchronised. */
+int bg_denoiser_create(int kind, int use_cf, const BgNamedTensor* weights, int n_weights, const float* sincos,
+                       void* stream, BgDenoiser** out);
+void bg_denoiser_destroy(BgDenoiser* m);
+
+typedef struct {
+  int B, S, E;                 /* batch, faces, edges per face (E = 0 for the surface nets) */
+  const float* x;              /* noisy input: surfPos (B,S,6) | surfZ (B,S,48) | edgePos (B,S,E,6) | edge (B,S,E,18) */
+  const int64_t* timesteps;    /* n_timesteps entries (1, or B) */
+  int n_timesteps;
+  const float* surfPos;        /* (B,S,6)    kinds 1,2,3 */
+  const float* surfZ;          /* (B,S,48)   kinds 2,3   */
+  const float* edgePos;        /* (B,S,E,6)  kind 3      */
+  const uint8_t* mask;         /* kind 1,2: (B,S) face mask; kind 3: (B,S,E) edge mask; nonzero = padded; may be NULL */
+  const int64_t* class_label;  /* (B,1) when created with use_cf, else NULL */
+  float* out;                  /* prediction, same shape as x, fp32 */
+} BgDenoiserArgs;
+
+size_t bg_denoiser_workspace_bytes(const BgDenoiser* m, int B, int S, int E);
+int bg_denoiser_forward(BgDenoiser* m, const BgDenoiserArgs* args, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Scheduler updates.  Replace diffusers DDPMScheduler.step / PNDMScheduler.step as called at
+ * sample.py:137,153,202,222,236,282 (arithmetic: SURVEY.md Appendix A.3/A.4).  Scalars are computed by the host-side
+ * scheduler object from its alphas_cumprod table exactly as diffusers does.
+ * ------------------------------------------------------------------------------------------------------------- */
+/* eps = eps_cond if eps_uncond == NULL else eps_cond*(1+w) - eps_uncond*w            (CFG, sample.py:134)
+ * x0  = clamp((x - sqrt_one_minus_abar*eps) / sqrt_abar, -clip, clip)  (clip <= 0: no clamp)
+ * out = c_x0*x0 + c_x*x + sigma*noise;   noise: explicit tensor, or Philox N(0,1) from (seed, offset) if NULL & sigma>0 */
+int bg_ddpm_step(const float* eps_cond, const float* eps_uncond, float cfg_w, const float* x, float* out,
+                 const float* noise, uint64_t seed, uint64_t offset, int64_t n, float sqrt_one_minus_abar,
+                 float sqrt_abar, float clip, float c_x0, float c_x, float sigma, void* stream);
+/* out = c_sample*x - c_eps*(w0*e0 + w1*e1 + w2*e2 + w3*e3)    (PNDM transfer + Adams-Bashforth / RK combination;
+ * unused e_i may be NULL with w_i = 0) */
+int bg_pndm_step(const float* x, float* out, int64_t n, float c_sample, float c_eps, const float* e0, float w0,
+                 const float* e1, float w1, const float* e2, float w2, const float* e3, float w3, void* stream);
+/* out = a*x + b*y  (y may be NULL); out = eps_cond*(1+w) - eps_uncond*w is bg_axpby(eps_c, 1+w, eps_u, -w) */
+int bg_axpby(const float* x, float a, const float* y, float b, float* out, int64_t n, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Unit-level entry points (used by tests and the bench to check/time individual kernels through the C ABI).
+ * ------------------------------------------------------------------------------------------------------------- */
+/* out[M,N] = act(A[M,K] (fp16) * W[N,K]^T (fp16) + bias + rowvec[row/rows_per_vec] + resid) */
+int bg_op_gemm_f16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, void* out, int ldo, int out_f16,
+                   int relu, const float* bias, const float* resid, int ldr, const float* rowvec, int rows_per_vec,
+                   int ldv, void* stream);
+/* qkv fp16 [B*L][2304] -> out fp16 [B*L][768]; key_mask (B,L) or NULL; use_block_list: skip fully padded key blocks
+ * (needs scratch_int of B*(ceil(L/128)+1) ints) */
+int bg_op_attention(const void* qkv, void* out, int B, int L, const uint8_t* key_mask, int use_block_list,
+                    int* scratch_int, void* stream);
+int bg_op_layernorm_f16(const float* x, int ldx, const float* gamma, const float* beta, void* y, int ldy, int rows,
+                        int act, void* stream);
+int bg_op_cast_f16(const float* x, void* y, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BREPGEN_B200_H_ */
