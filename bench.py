@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py -- B-reps/sec of the 1000-step-per-stage ABC cascade (BASELINE.json), one process per GPU.
+
+    python bench.py --gpus 1 --steps 3 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+    python bench.py --impl reference ...        # the reference's algorithm on the host cores (oracle port), same metric
+
+Workload (BASELINE.json configs[2]): full ABC cascade, batch 256 per GPU, S0 = 50 -> S = 100 faces,
+E = 40 edges/face (edge-stage sequences of 4000 tokens), dense masks, random-init weights, Gaussian inputs.
+One bench "step" = one pass of the whole cascade (SurfPos -> SurfZ -> EdgePos -> EdgeZ, every stage a DDPM loop of
+T = --steps-per-stage network evaluations + fused scheduler updates, then both VAE decodes when available) over one batch.
+Every DDPM step of a stage costs the same work whatever its t, so the metric (defined at T = 1000) is reported as
+    value = n_gpus * B / (seconds_per_step * 1000 / T)
+with T stated in `config`; `--steps-per-stage 1000` runs the literal thing (minutes per step at B = 256).
+Weak scaling: every rank runs its own batch of B; no collective on the hot path.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "B-reps/sec (1000-step ABC cascade)"
+UNIT = "B-reps/s"
+KINDS = ("surfpos", "surfz", "edgepos", "edgez")
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="B-reps per GPU")
+    ap.add_argument("--surfaces", type=int, default=50)
+    ap.add_argument("--edges", type=int, default=40)
+    ap.add_argument("--steps-per-stage", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 1590.0, 1400.0, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------ algorithmic FLOPs
+def encoder_flops(L):   # per sample, per forward, dense, mul-add = 2
+    return 12 * (L * 7_864_320 + 3072 * L * L)
+
+
+def mlp_flops(d_in, d_out):
+    return 2 * d_in * 768 + 2 * 768 * d_out
+
+
+def cascade_flops_per_brep(S0, S, E, steps=1000):
+    sp = lambda s: encoder_flops(s) + s * (mlp_flops(6, 768) + mlp_flops(768, 6))
+    sz = encoder_flops(S) + S * (mlp_flops(48, 768) + mlp_flops(6, 768) + mlp_flops(768, 48))
+    ep = encoder_flops(S * E) + S * (mlp_flops(6, 768) + mlp_flops(48, 768)) + S * E * (mlp_flops(6, 768) + mlp_flops(768, 6))
+    ez = encoder_flops(S * E) + S * (mlp_flops(6, 768) + mlp_flops(48, 768)) + S * E * (2 * mlp_flops(6, 768) + mlp_flops(12, 768) + mlp_flops(768, 18))
+    return steps * (0.75 * sp(S0) + 0.25 * sp(S) + sz + ep + ez)
+
+
+# ------------------------------------------------------------------------------------------------ CPU baseline (oracle port)
+def cpu_reference_sample(S0, S, E, reps):
+    """Times the oracle (CPU fp32 restatement of the reference, pinned to its own classes) on the host cores: per stage,
+    one forward + scheduler step at batch 1, `reps` timed repetitions after one warm-up; extrapolated to the
+    4 x 1000-step cascade.  Returns (B-reps/s, cores, description)."""
+    from brepgen_b200.spec import denoiser_spec
+    from brepgen_b200.synth import synth_state_dict
+    from oracle import denoisers as O
+    from oracle.schedulers import DDPMOracle
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    orc = DDPMOracle()
+    g = torch.Generator().manual_seed(0)
+    r = lambda *s: torch.randn(*s, generator=g)
+    t = torch.tensor([500])
+    per = {}
+    with torch.no_grad():
+        for name, kind, shape in (("surfpos@S0", "surfpos", (1, S0, 6)), ("surfpos@S", "surfpos", (1, S, 6)),
+                                  ("surfz", "surfz", (1, S, 48)), ("edgepos", "edgepos", (1, S, E, 6)),
+                                  ("edgez", "edgez", (1, S, E, 18))):
+            sd = synth_state_dict(denoiser_spec(kind, False), seed=1)
+            x = r(*shape)
+            sP, sZ, eP = r(1, shape[1], 6), r(1, shape[1], 48), r(1, shape[1], E, 6)
+            fm = torch.zeros(1, shape[1], dtype=torch.bool)
+            em = torch.zeros(1, shape[1], E, dtype=torch.bool)
+            fwd = {"surfpos": lambda: O.surfpos_forward(sd, x, t), "surfz": lambda: O.surfz_forward(sd, x, t, sP, fm),
+                   "edgepos": lambda: O.edgepos_forward(sd, x, t, sP, sZ, fm),
+                   "edgez": lambda: O.edgez_forward(sd, x, t, eP, sP, sZ, em)}[kind]
+            orc.step(fwd(), 500, x, r(*shape))
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                orc.step(fwd(), 500, x, r(*shape))
+            per[name] = (time.perf_counter() - t0) / reps
+            del sd
+    sec_per_brep = 750 * per["surfpos@S0"] + 250 * per["surfpos@S"] + 1000 * (per["surfz"] + per["edgepos"] + per["edgez"])
+    desc = ("oracle fp32 (torch CPU), batch 1, 1 warm + %d timed (forward + DDPM step) per stage; s/step: " % reps +
+            ", ".join(f"{k}={v:.3f}" for k, v in per.items()) + "; extrapolated to 750/250 + 3x1000 steps")
+    return 1.0 / sec_per_brep, cores, desc
+
+
+# ------------------------------------------------------------------------------------------------ clocks sampler
+class Clocks(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop = index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def finish(self):
+        self._stop.set()
+        self.join(timeout=3)
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        mx = max((int(r[1]) for r in self.rows if r[1].isdigit()), default=None)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ main arms
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    S0, E = args.surfaces, args.edges
+    S = 2 * S0
+    vals = []
+    for _ in range(max(args.warmup, 0)):
+        cpu_reference_sample(S0, S, E, 1)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        v, cores, desc = cpu_reference_sample(S0, S, E, 1)
+        vals.append(v)
+    ms = (time.perf_counter() - t0) / max(args.steps, 1) * 1e3
+    v = sum(vals) / len(vals)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"abc_cascade S0={S0}->S={S} E={E} L_edge={S * E}, dense masks, 4x1000 DDPM steps",
+                       "note": "reference algorithm on host cores (its CUDA path needs diffusers/OCC, absent offline)"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    from brepgen_b200 import _ffi
+    from brepgen_b200.models import NETS
+    from brepgen_b200.sampler import Cascade, CascadeConfig
+    from brepgen_b200.spec import denoiser_spec
+    from brepgen_b200.synth import synth_state_dict
+    _ffi.check(_ffi.lib().bg_check_device(), "bg_check_device")
+
+    B, S0, E, T = args.batch, args.surfaces, args.edges, args.steps_per_stage
+    S = 2 * S0
+    models = {}
+    for kind in KINDS:
+        m = NETS[kind](False)
+        m.load_state_dict(synth_state_dict(denoiser_spec(kind, False), seed=1))
+        models[kind] = m.to(dev).eval()
+    surf_vae = edge_vae = None
+    try:
+        from brepgen_b200.vae import build_synthetic_decoders
+        surf_vae, edge_vae = build_synthetic_decoders(dev)
+    except ImportError:
+        pass
+    casc = Cascade(models, surf_vae, edge_vae, device=dev)
+    cfg = CascadeConfig(batch_size=B, num_surfaces=S0, num_edges=E, schedule="ddpm", ddpm_steps=T, dense_masks=True,
+                        seed=1000 + rank, decode=surf_vae is not None)
+    g = torch.Generator().manual_seed(1000 + rank)
+    shapes = {"surfPos": (B, S0, 6), "surfZ": (B, S, 48), "edgePos": (B, S, E, 6), "edgeZV": (B, S, E, 18)}
+    host_in = {k: torch.randn(s, generator=g).pin_memory() for k, s in shapes.items()}
+    dev_in = {k: v.to(dev) for k, v in host_in.items()}
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / k
+        if dist is not None:
+            tms = torch.tensor([ms], device=dev)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ms = float(tms)
+        barrier()
+        return ms
+
+    step_resident = lambda: casc.run(cfg, init_noise=dev_in)
+    for _ in range(args.warmup):
+        step_resident()
+    clocks = Clocks(local)
+    clocks.start()
+    l0 = _ffi.lib().bg_launch_count()
+    ms = timed(step_resident, args.steps)
+    launches = _ffi.lib().bg_launch_count() - l0
+    clk = clocks.finish()
+    scale = 1000.0 / T
+    value = world * B / (ms / 1e3 * scale)
+
+    # end to end through the public API: pinned host noise in, every output back to pinned host memory, per step
+    e2e = None
+    if not args.no_e2e:
+        host_out = {}
+
+        def step_e2e():
+            din = {k: v.to(dev, non_blocking=True) for k, v in host_in.items()}
+            out = casc.run(cfg, init_noise=din)
+            for k, v in out.items():
+                if k not in host_out:
+                    host_out[k] = torch.empty(v.shape, dtype=v.dtype).pin_memory()
+                host_out[k].copy_(v, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        step_e2e()
+        ms_e = timed(step_e2e, args.steps)
+        h2d = sum(v.numel() * v.element_size() for v in host_in.values())
+        d2h = sum(v.numel() * v.element_size() for v in host_out.values())
+        e2e = {"value": world * B / (ms_e / 1e3 * scale), "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": ms_e}
+
+    # roofline of the dominant kernel (edge-stage flash attention, L = S*E), timed alone with CUDA events
+    burst, sustained, src = peaks()
+    L = S * E
+    qkv = (torch.randn(B * L, 2304, device=dev, dtype=torch.float16))
+    ao = torch.empty(B * L, 768, device=dev, dtype=torch.float16)
+    attn = lambda: _ffi.check(_ffi.lib().bg_op_attention(qkv.data_ptr(), ao.data_ptr(), B, L, None, 0, None,
+                                                          _ffi.current_stream()))
+    for _ in range(2):
+        attn()
+    ms_attn = timed(attn, 5)
+    fl_attn = B * 3072.0 * L * L
+    ach = fl_attn / (ms_attn / 1e3) / 1e12
+    del qkv, ao
+    roofline = {"bound": "tensor", "kernel": "attn_kernel<2> (tcgen05 flash attention, B=%d L=%d)" % (B, L),
+                "achieved": ach, "peak": burst, "unit": "TFLOP/s", "frac": ach / burst, "peak_source": f"bf16_tflops burst, {src}",
+                "traffic": None, "ms_per_launch": ms_attn, "flop_per_launch": fl_attn}
+    flops_brep = cascade_flops_per_brep(S0, S, E)
+    whole = {"algorithmic_tflop_per_brep": flops_brep / 1e12, "achieved_tflops_per_gpu": value / world * flops_brep / 1e12,
+             "frac_of_sustained_peak": value / world * flops_brep / 1e12 / sustained}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, cores, desc = cpu_reference_sample(S0, S, E, 2)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f16 x f16 -> f32 (tcgen05 kind::f16; split hi+lo weights on in/out-proj; fp32 residual/LN/softmax)",
+                "data": "synthetic",
+                "config": {"workload": f"abc_cascade B={B}/GPU S0={S0}->S={S} E={E} L_edge={L}, dense masks",
+                           "ddpm_steps_per_stage_timed": T, "value_normalised_to_steps_per_stage": 1000,
+                           "vae_decode_in_step": surf_vae is not None,
+                           "l2": "activations of one step (GBs) exceed the 126 MB L2; no explicit flush",
+                           "precision": models["surfpos"].precision, "parallelism": f"batch-sharded x{world}, no collective"},
+                "roofline": roofline, "whole_cascade": whole, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+                "clocks": clk}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

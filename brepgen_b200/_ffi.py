@@ -28,13 +28,16 @@ SIGNATURES = {
     "bg_version": (i32, []),
     "bg_last_error": (C.c_char_p, []),
     "bg_check_device": (i32, []),
-    "bg_denoiser_create": (i32, [i32, i32, C.POINTER(BgNamedTensor), i32, vp, vp, C.POINTER(vp)]),
+    "bg_launch_count": (u64, []),
+    "bg_denoiser_create": (i32, [i32, i32, i32, C.POINTER(BgNamedTensor), i32, vp, vp, C.POINTER(vp)]),
     "bg_denoiser_destroy": (None, [vp]),
     "bg_denoiser_workspace_bytes": (sz, [vp, i32, i32, i32]),
     "bg_denoiser_forward": (i32, [vp, C.POINTER(BgDenoiserArgs), vp, sz, vp]),
     "bg_ddpm_step": (i32, [vp, vp, f32, vp, vp, vp, u64, u64, i64, f32, f32, f32, f32, f32, f32, vp]),
     "bg_pndm_step": (i32, [vp, vp, i64, f32, f32, vp, f32, vp, f32, vp, f32, vp, f32, vp]),
     "bg_axpby": (i32, [vp, f32, vp, f32, vp, i64, vp]),
+    "bg_dedup_surfaces": (i32, [vp, i32, i32, f32, vp, vp, vp]),
+    "bg_dedup_edges": (i32, [vp, vp, i32, i32, i32, f32, vp, vp]),
     "bg_op_gemm_f16": (i32, [vp, i32, vp, i32, i32, i32, i32, vp, i32, i32, i32, vp, vp, i32, vp, i32, i32, vp]),
     "bg_op_attention": (i32, [vp, vp, i32, i32, vp, i32, vp, vp]),
     "bg_op_layernorm_f16": (i32, [vp, i32, vp, vp, vp, i32, i32, i32, vp]),

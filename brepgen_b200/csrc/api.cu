@@ -13,6 +13,8 @@ int bg_version(void) { return 100; }   // 0.1.0
 
 const char* bg_last_error(void) { return last_error_cstr(); }
 
+uint64_t bg_launch_count(void) { return launch_count(); }
+
 int bg_check_device(void) {
   int dev = 0, major = 0, minor = 0;
   BG_CUDA(cudaGetDevice(&dev));

@@ -350,7 +350,7 @@ int launch_nt(cudaStream_t st, const CUtensorMap& tm, const AttnParams& p) {
   const int nq = (p.L + 127) / 128;
   dim3 grid((nq + NT - 1) / NT, NHEAD, p.B);
   attn_kernel<NT><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(tm, p);
-  return check_cuda(cudaGetLastError(), "attn_kernel launch");
+  return check_launch("attn_kernel launch");
 }
 
 }  // namespace
@@ -372,7 +372,7 @@ int launch_build_block_list(cudaStream_t st, const uint8_t* key_mask, int B, int
   BG_REQUIRE(key_mask && blk_list && blk_count && B > 0 && L > 0, "block list: bad arguments");
   const int nkb = (L + 127) / 128;
   block_list_kernel<<<B, 128, nkb * sizeof(int), st>>>(key_mask, L, nkb, blk_list, blk_count);
-  return check_cuda(cudaGetLastError(), "block_list_kernel launch");
+  return check_launch("block_list_kernel launch");
 }
 
 }  // namespace bg

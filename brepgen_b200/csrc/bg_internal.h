@@ -21,6 +21,8 @@ enum Status : int {
 };
 int set_error(int code, const std::string& msg);
 int check_cuda(cudaError_t e, const char* what);
+int check_launch(const char* what);          // cudaGetLastError() after a kernel launch; counts the launch
+unsigned long long launch_count();
 #define BG_CUDA(x)                                              \
   do {                                                          \
     int _s = ::bg::check_cuda((x), #x);                         \
@@ -58,6 +60,7 @@ struct GemmEpilogue {
   const float* rowvec = nullptr; // fp32 [(M / rows_per_vec), ldv]: row r adds rowvec[r / rows_per_vec]
   int rows_per_vec = 1;
   int ldv = 0;
+  int a_kwrap = 0;               // >0: A has a_kwrap columns and is reused cyclically along K (split-weight GEMM)
 };
 int launch_gemm_f16(cudaStream_t st, const __half* A, int lda, const __half* W, int ldw, int M, int N, int K,
                     const GemmEpilogue& ep);
@@ -78,14 +81,15 @@ int launch_build_block_list(cudaStream_t st, const uint8_t* key_mask, int B, int
 
 // ---- CUDA-core kernels (HBM-bound glue) ----
 // y[row, 0:768] (fp16, pitch ldy) = act(LayerNorm(x[row, 0:768]) * g + b); act: 0 none, 1 SiLU.   eps = 1e-5
+// lo_offset > 0: additionally writes the fp16 rounding residual (value - fp16(value)) at y[row, lo_offset + c]
 int launch_layernorm_f16(cudaStream_t st, const float* x, int ldx, const float* g, const float* b, __half* y, int ldy,
-                         int rows, int act);
+                         int rows, int act, int lo_offset = 0);
 // y (fp16, pitch ldy) = SiLU(LayerNorm(x[row,0:d_in] * W0^T + b0)); W0t is [d_in][768] fp32 (transposed Linear weight)
 int launch_embed_in(cudaStream_t st, const float* x, int ldx, int d_in, const float* W0t, const float* b0, const float* g,
                     const float* b, __half* y, int ldy, int rows);
-// out[row, 0:d_out] (fp32) = h[row, 0:768] (fp16) * W^T + bias;  W [d_out][768] fp32, d_out <= 64
-int launch_head_out(cudaStream_t st, const __half* h, int ldh, const float* W, const float* bias, float* out, int d_out,
-                    int rows);
+// out[row, 0:d_out] (fp32) = SiLU(LayerNorm(x[row, 0:768])) * W^T + bias, all fp32;  W [d_out][768], d_out <= 64
+int launch_ln_silu_head(cudaStream_t st, const float* x, int ldx, const float* g, const float* b, const float* W,
+                        const float* bias, float* out, int d_out, int rows);
 // cond[b, :] = time_table[t_b, :] + (class_table ? class_table[label_b, :] : 0);  t: int64 [n_t] (n_t = 1 or B)
 int launch_cond(cudaStream_t st, const float* time_table, const int64_t* t, int n_t, const float* class_table,
                 const int64_t* label, float* cond, int B);

@@ -18,6 +18,13 @@ int check_cuda(cudaError_t e, const char* what) {
   return set_error(BG_ERR_CUDA, std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")");
 }
 
+static unsigned long long g_launches = 0;   // kernels launched by this library (host-side counter, single host thread)
+int check_launch(const char* what) {
+  ++g_launches;
+  return check_cuda(cudaGetLastError(), what);
+}
+unsigned long long launch_count() { return g_launches; }
+
 int num_sms() {
   static int cached = 0;
   if (cached == 0) {

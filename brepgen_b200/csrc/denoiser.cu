@@ -44,7 +44,8 @@ const KindDef KINDS[4] = {
 };
 
 struct LayerW {
-  __half *wqkv, *wo, *w1, *w2;
+  __half *wqkv, *wo, *w1, *w2;   // [N][k*] fp16; k* = K (single) or 2K ([W_hi | W_lo], split-weight GEMM)
+  int kqkv, ko, k1, k2;
   float *bqkv, *bo, *b1, *b2, *ln1g, *ln1b, *ln2g, *ln2b;
 };
 
@@ -65,6 +66,18 @@ __global__ void pack_cat_kernel(const float* __restrict__ w, __half* __restrict_
   if (i < D * D) {
     const int n = i / D, k = i % D;
     wcat[(size_t)n * ldcat + col0 + k] = __float2half_rn(w[i]);
+  }
+}
+// dst[n, col0 + k] = hi or lo part of w[n, k]:  hi = fp16(w), lo = fp16(w - float(hi))  (lo is ~2^-11 |w|; fp16
+// subnormals keep it to ~1 % which is all the compensation needs)
+__global__ void pack_split_kernel(const float* __restrict__ w, __half* __restrict__ dst, int N, int K, int ld, int col0,
+                                  int part) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (size_t)N * K) {
+    const int n = (int)(i / K), k = (int)(i % K);
+    const float v = w[i];
+    const __half hi = __float2half_rn(v);
+    dst[(size_t)n * ld + col0 + k] = part == 0 ? hi : __float2half_rn(v - __half2float(hi));
   }
 }
 __global__ void add_vec_kernel(float* __restrict__ acc, const float* __restrict__ v, int n) {
@@ -124,6 +137,7 @@ using namespace bg;
 
 struct BgDenoiser {
   int kind = 0, use_cf = 0;
+  int precision = 1;           // 0: plain fp16 operands; 1: + split in/out-proj weights + compensated fc_out; 2: all split
   char* arena = nullptr;       // one device allocation holding every packed tensor
   size_t arena_bytes = 0;
   LayerW layer[NLAYER];
@@ -183,6 +197,20 @@ struct Packer {
     if (!dry && src && !err) err = launch_cast_f32_to_f16(st, src, dst, (size_t)numel);
     return dst;
   }
+  // [N][K] fp32 -> fp16 [N][K] (split == 0) or [N][2K] = [W_hi | W_lo]; returns the packed K through *k_out
+  __half* pack_weight(const std::string& name, int N, int K, bool split, int* k_out) {
+    const float* src = find(name, (int64_t)N * K);
+    const int kp = split ? 2 * K : K;
+    *k_out = kp;
+    __half* dst = take<__half>((size_t)N * kp);
+    if (!dry && src && !err) {
+      const unsigned blocks = (unsigned)(((size_t)N * K + 255) / 256);
+      pack_split_kernel<<<blocks, 256, 0, st>>>(src, dst, N, K, kp, 0, 0);
+      if (split) pack_split_kernel<<<blocks, 256, 0, st>>>(src, dst, N, K, kp, K, 1);
+      err = check_launch("pack_split_kernel");
+    }
+    return dst;
+  }
 };
 
 int pack(BgDenoiser* m, Packer& pk, const float* sincos) {
@@ -190,13 +218,14 @@ int pack(BgDenoiser* m, Packer& pk, const float* sincos) {
   for (int i = 0; i < NLAYER; ++i) {
     const std::string p = "net.layers." + std::to_string(i) + ".";
     LayerW& L = m->layer[i];
-    L.wqkv = pk.cast_f16(p + "self_attn.in_proj_weight", 3LL * D * D);
+    const bool s_attn = m->precision >= 1, s_ff = m->precision >= 2;
+    L.wqkv = pk.pack_weight(p + "self_attn.in_proj_weight", 3 * D, D, s_attn, &L.kqkv);
     L.bqkv = pk.copy_f32(p + "self_attn.in_proj_bias", 3 * D);
-    L.wo = pk.cast_f16(p + "self_attn.out_proj.weight", 1LL * D * D);
+    L.wo = pk.pack_weight(p + "self_attn.out_proj.weight", D, D, s_attn, &L.ko);
     L.bo = pk.copy_f32(p + "self_attn.out_proj.bias", D);
-    L.w1 = pk.cast_f16(p + "linear1.weight", 1LL * FF * D);
+    L.w1 = pk.pack_weight(p + "linear1.weight", FF, D, s_ff, &L.k1);
     L.b1 = pk.copy_f32(p + "linear1.bias", FF);
-    L.w2 = pk.cast_f16(p + "linear2.weight", 1LL * D * FF);
+    L.w2 = pk.pack_weight(p + "linear2.weight", D, FF, s_ff, &L.k2);
     L.b2 = pk.copy_f32(p + "linear2.bias", D);
     L.ln1g = pk.copy_f32(p + "norm1.weight", D);
     L.ln1b = pk.copy_f32(p + "norm1.bias", D);
@@ -238,11 +267,24 @@ int pack(BgDenoiser* m, Packer& pk, const float* sincos) {
       pack_cat_kernel<<<(D * D + 255) / 256, 256, 0, pk.st>>>(w3, tok ? m->wcat_tok : m->wcat_face,
                                                                (tok ? m->n_tok : m->n_face) * D, slot * D);
       add_vec_kernel<<<(D + 255) / 256, 256, 0, pk.st>>>(tok ? m->bcat_tok : m->bcat_face, b3, D);
-      pk.err = check_cuda(cudaGetLastError(), "pack embed");
+      pk.err = check_launch("pack embed");
     }
     (e.level == 0 ? i_tok : i_face)++;
   }
-  m->fc0w = pk.cast_f16("fc_out.0.weight", 1LL * D * D);
+  if (m->precision >= 1) {
+    // compensated product: [x_hi | x_lo | x_hi] * [W_hi | W_hi | W_lo]^T  (drops only the lo*lo term, ~2^-22)
+    const float* src = pk.find("fc_out.0.weight", 1LL * D * D);
+    m->fc0w = pk.take<__half>((size_t)D * 3 * D);
+    if (!pk.dry && src && !pk.err) {
+      const unsigned blocks = (D * D + 255) / 256;
+      pack_split_kernel<<<blocks, 256, 0, pk.st>>>(src, m->fc0w, D, D, 3 * D, 0, 0);
+      pack_split_kernel<<<blocks, 256, 0, pk.st>>>(src, m->fc0w, D, D, 3 * D, D, 0);
+      pack_split_kernel<<<blocks, 256, 0, pk.st>>>(src, m->fc0w, D, D, 3 * D, 2 * D, 1);
+      pk.err = check_launch("pack fc_out.0");
+    }
+  } else {
+    m->fc0w = pk.cast_f16("fc_out.0.weight", 1LL * D * D);
+  }
   m->fc0b = pk.copy_f32("fc_out.0.bias", D);
   m->fclng = pk.copy_f32("fc_out.1.weight", D);
   m->fclnb = pk.copy_f32("fc_out.1.bias", D);
@@ -265,7 +307,7 @@ int pack(BgDenoiser* m, Packer& pk, const float* sincos) {
     }
     if (!pk.err) {
       mlp_table_kernel<<<NT_TABLE, 256, 0, pk.st>>>(sc, tw0, tb0, tg, tb, tw3, tb3, m->time_table);
-      pk.err = check_cuda(cudaGetLastError(), "time table");
+      pk.err = check_launch("time table");
     }
   }
   if (m->use_cf) m->class_table = pk.copy_f32("class_embed.embed.weight", (int64_t)NCLASS * D);
@@ -310,13 +352,15 @@ Workspace carve(char* base, int kind, int B, int S, int E) {
 
 extern "C" {
 
-int bg_denoiser_create(int kind, int use_cf, const BgNamedTensor* weights, int n_weights, const float* sincos,
-                       void* stream, BgDenoiser** out) {
+int bg_denoiser_create(int kind, int use_cf, int precision, const BgNamedTensor* weights, int n_weights,
+                       const float* sincos, void* stream, BgDenoiser** out) {
   BG_REQUIRE(kind >= 0 && kind < 4 && weights && n_weights > 0 && out, "denoiser_create: bad arguments");
+  BG_REQUIRE(precision >= 0 && precision <= 2, "denoiser_create: precision must be 0, 1 or 2");
   BG_TRY(bg_check_device());
   BgDenoiser* m = new BgDenoiser();
   m->kind = kind;
   m->use_cf = use_cf ? 1 : 0;
+  m->precision = precision;
   Packer pk;
   for (int i = 0; i < n_weights; ++i) pk.by_name[weights[i].name] = &weights[i];
   pk.st = reinterpret_cast<cudaStream_t>(stream);
@@ -429,7 +473,8 @@ int bg_denoiser_forward(BgDenoiser* m, const BgDenoiserArgs* a, void* workspace,
     {
       GemmEpilogue ep;
       ep.out = w.QKV; ep.ldo = 3 * D; ep.out_f16 = 1; ep.bias = Lw.bqkv;
-      BG_TRY(launch_gemm_f16(st, w.Xn, D, Lw.wqkv, D, M, 3 * D, D, ep));
+      ep.a_kwrap = Lw.kqkv > D ? D : 0;
+      BG_TRY(launch_gemm_f16(st, w.Xn, D, Lw.wqkv, Lw.kqkv, M, 3 * D, Lw.kqkv, ep));
     }
     {
       AttnArgs at;
@@ -441,30 +486,40 @@ int bg_denoiser_forward(BgDenoiser* m, const BgDenoiserArgs* a, void* workspace,
     {
       GemmEpilogue ep;
       ep.out = w.X; ep.ldo = D; ep.out_f16 = 0; ep.bias = Lw.bo; ep.resid = w.X; ep.ldr = D;
-      BG_TRY(launch_gemm_f16(st, w.AO, D, Lw.wo, D, M, D, D, ep));
+      ep.a_kwrap = Lw.ko > D ? D : 0;
+      BG_TRY(launch_gemm_f16(st, w.AO, D, Lw.wo, Lw.ko, M, D, Lw.ko, ep));
     }
     BG_TRY(launch_layernorm_f16(st, w.X, D, Lw.ln2g, Lw.ln2b, w.Xn, D, M, 0));
     {
       GemmEpilogue ep;
       ep.out = w.Hff; ep.ldo = FF; ep.out_f16 = 1; ep.relu = 1; ep.bias = Lw.b1;
-      BG_TRY(launch_gemm_f16(st, w.Xn, D, Lw.w1, D, M, FF, D, ep));
+      ep.a_kwrap = Lw.k1 > D ? D : 0;
+      BG_TRY(launch_gemm_f16(st, w.Xn, D, Lw.w1, Lw.k1, M, FF, Lw.k1, ep));
     }
     {
       GemmEpilogue ep;
       ep.out = w.X; ep.ldo = D; ep.out_f16 = 0; ep.bias = Lw.b2; ep.resid = w.X; ep.ldr = D;
-      BG_TRY(launch_gemm_f16(st, w.Hff, FF, Lw.w2, FF, M, D, FF, ep));
+      ep.a_kwrap = Lw.k2 > FF ? FF : 0;
+      BG_TRY(launch_gemm_f16(st, w.Hff, FF, Lw.w2, Lw.k2, M, D, Lw.k2, ep));
     }
   }
 
-  // 5. final norm + fc_out (Linear -> LN -> SiLU -> Linear(768, d_out))
-  BG_TRY(launch_layernorm_f16(st, w.X, D, m->normg, m->normb, w.Xn, D, M, 0));
+  // 5. final norm + fc_out (Linear -> LN -> SiLU -> Linear(768, d_out)); this tail feeds the output directly, so at
+  //    precision >= 1 it runs as a compensated fp16 product (hi/lo activations x hi/lo weights) and an fp32 head.
   {
     GemmEpilogue ep;
     ep.out = w.X; ep.ldo = D; ep.out_f16 = 0; ep.bias = m->fc0b;
-    BG_TRY(launch_gemm_f16(st, w.Xn, D, m->fc0w, D, M, D, D, ep));
+    if (m->precision >= 1) {
+      __half* A3 = w.QKV;   // [M][2304] scratch: cols 0..767 hi, 768..1535 lo (the third K block wraps back to hi)
+      BG_TRY(launch_layernorm_f16(st, w.X, D, m->normg, m->normb, A3, 3 * D, M, 0, D));
+      ep.a_kwrap = 2 * D;
+      BG_TRY(launch_gemm_f16(st, A3, 3 * D, m->fc0w, 3 * D, M, D, 3 * D, ep));
+    } else {
+      BG_TRY(launch_layernorm_f16(st, w.X, D, m->normg, m->normb, w.Xn, D, M, 0));
+      BG_TRY(launch_gemm_f16(st, w.Xn, D, m->fc0w, D, M, D, D, ep));
+    }
   }
-  BG_TRY(launch_layernorm_f16(st, w.X, D, m->fclng, m->fclnb, w.Xn, D, M, 1));
-  BG_TRY(launch_head_out(st, w.Xn, D, m->fc3w, m->fc3b, a->out, kd.d_out, M));
+  BG_TRY(launch_ln_silu_head(st, w.X, D, m->fclng, m->fclnb, m->fc3w, m->fc3b, a->out, kd.d_out, M));
   return BG_OK;
 }
 

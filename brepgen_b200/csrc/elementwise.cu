@@ -48,7 +48,7 @@ __device__ __forceinline__ void ln_row(float (&v)[24], const float* __restrict__
   }
 }
 
-__device__ __forceinline__ void store_row_f16(const float (&v)[24], __half* y, int lane) {
+__device__ __forceinline__ void store_row_f16(const float (&v)[24], __half* y, int lane, int lo_offset = 0) {
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
     __half2 h0 = __floats2half2_rn(v[4 * j], v[4 * j + 1]);
@@ -57,12 +57,20 @@ __device__ __forceinline__ void store_row_f16(const float (&v)[24], __half* y, i
     u.x = *reinterpret_cast<uint32_t*>(&h0);
     u.y = *reinterpret_cast<uint32_t*>(&h1);
     *reinterpret_cast<uint2*>(y + lane * 4 + 128 * j) = u;
+    if (lo_offset > 0) {   // rounding residual, exactly representable difference of two nearby floats
+      const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+      __half2 l0 = __floats2half2_rn(v[4 * j] - f0.x, v[4 * j + 1] - f0.y);
+      __half2 l1 = __floats2half2_rn(v[4 * j + 2] - f1.x, v[4 * j + 3] - f1.y);
+      u.x = *reinterpret_cast<uint32_t*>(&l0);
+      u.y = *reinterpret_cast<uint32_t*>(&l1);
+      *reinterpret_cast<uint2*>(y + lo_offset + lane * 4 + 128 * j) = u;
+    }
   }
 }
 
 __global__ void __launch_bounds__(256) layernorm_f16_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ g,
                                                             const float* __restrict__ b, __half* __restrict__ y, int ldy,
-                                                            int rows, int act) {
+                                                            int rows, int act, int lo_offset) {
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
@@ -74,7 +82,7 @@ __global__ void __launch_bounds__(256) layernorm_f16_kernel(const float* __restr
       v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
     }
     ln_row(v, g, b, lane, act);
-    store_row_f16(v, y + (size_t)row * ldy, lane);
+    store_row_f16(v, y + (size_t)row * ldy, lane, lo_offset);
   }
 }
 
@@ -110,10 +118,12 @@ __global__ void __launch_bounds__(256) embed_in_kernel(const float* __restrict__
   }
 }
 
-// out[row, o] = bias[o] + sum_k h[row,k] W[o,k];  warp per row, W (fp32 [d_out][768]) staged in shared memory
-__global__ void __launch_bounds__(256) head_out_kernel(const __half* __restrict__ h, int ldh, const float* __restrict__ W,
-                                                       const float* __restrict__ bias, float* __restrict__ out, int d_out,
-                                                       int rows) {
+// out[row, o] = bias[o] + sum_k SiLU(LN(x[row]))[k] W[o,k];  all fp32; warp per row, W ([d_out][768]) in shared memory.
+// (fc_out.1 -> SiLU -> fc_out.3 of network.py:1094-1099; fused so the hidden vector never leaves registers.)
+__global__ void __launch_bounds__(256) ln_silu_head_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ g,
+                                                           const float* __restrict__ b, const float* __restrict__ W,
+                                                           const float* __restrict__ bias, float* __restrict__ out, int d_out,
+                                                           int rows) {
   extern __shared__ float sW[];   // [d_out][768]
   for (int i = threadIdx.x; i < d_out * D / 4; i += blockDim.x)
     reinterpret_cast<float4*>(sW)[i] = __ldg(reinterpret_cast<const float4*>(W) + i);
@@ -121,15 +131,14 @@ __global__ void __launch_bounds__(256) head_out_kernel(const __half* __restrict_
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
-    const __half* hr = h + (size_t)row * ldh;
+    const float* xr = x + (size_t)row * ldx;
     float v[24];
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
-      const uint2 u = *reinterpret_cast<const uint2*>(hr + lane * 4 + 128 * j);
-      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
-      const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
-      v[4 * j] = a.x; v[4 * j + 1] = a.y; v[4 * j + 2] = c.x; v[4 * j + 3] = c.y;
+      const float4 t = *reinterpret_cast<const float4*>(xr + lane * 4 + 128 * j);
+      v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
     }
+    ln_row(v, g, b, lane, 1);
     float mine = 0.f;
     for (int o = 0; o < d_out; ++o) {
       const float* wr = sW + o * D;
@@ -195,32 +204,32 @@ inline int row_grid(int rows, int wpb) {
 }  // namespace
 
 int launch_layernorm_f16(cudaStream_t st, const float* x, int ldx, const float* g, const float* b, __half* y, int ldy,
-                         int rows, int act) {
-  BG_REQUIRE(rows > 0 && ldx % 4 == 0 && ldy % 4 == 0, "layernorm: bad shape");
-  layernorm_f16_kernel<<<row_grid(rows, 8), 256, 0, st>>>(x, ldx, g, b, y, ldy, rows, act);
-  return check_cuda(cudaGetLastError(), "layernorm_f16_kernel launch");
+                         int rows, int act, int lo_offset) {
+  BG_REQUIRE(rows > 0 && ldx % 4 == 0 && ldy % 4 == 0 && lo_offset % 4 == 0, "layernorm: bad shape");
+  layernorm_f16_kernel<<<row_grid(rows, 8), 256, 0, st>>>(x, ldx, g, b, y, ldy, rows, act, lo_offset);
+  return check_launch("layernorm_f16_kernel launch");
 }
 
 int launch_embed_in(cudaStream_t st, const float* x, int ldx, int d_in, const float* W0t, const float* b0, const float* g,
                     const float* b, __half* y, int ldy, int rows) {
   BG_REQUIRE(rows > 0 && d_in > 0 && ldy % 4 == 0, "embed_in: bad shape");
   embed_in_kernel<<<row_grid(rows, 8), 256, 0, st>>>(x, ldx, d_in, W0t, b0, g, b, y, ldy, rows);
-  return check_cuda(cudaGetLastError(), "embed_in_kernel launch");
+  return check_launch("embed_in_kernel launch");
 }
 
-int launch_head_out(cudaStream_t st, const __half* h, int ldh, const float* W, const float* bias, float* out, int d_out,
-                    int rows) {
-  BG_REQUIRE(rows > 0 && d_out > 0 && d_out <= 64 && ldh % 4 == 0, "head_out: bad shape");
+int launch_ln_silu_head(cudaStream_t st, const float* x, int ldx, const float* g, const float* b, const float* W,
+                        const float* bias, float* out, int d_out, int rows) {
+  BG_REQUIRE(rows > 0 && d_out > 0 && d_out <= 64 && ldx % 4 == 0, "ln_silu_head: bad shape");
   const int smem = d_out * D * 4;
-  static int configured_for = 0;
-  if (smem > 48 * 1024 && configured_for < smem) {
-    BG_CUDA(cudaFuncSetAttribute(head_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * D * 4));
-    configured_for = 64 * D * 4;
+  static bool configured = false;
+  if (!configured) {
+    BG_CUDA(cudaFuncSetAttribute(ln_silu_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * D * 4));
+    configured = true;
   }
   const int want = (rows + 7) / 8;
   const int cap = num_sms() * 2;
-  head_out_kernel<<<want < cap ? want : cap, 256, smem, st>>>(h, ldh, W, bias, out, d_out, rows);
-  return check_cuda(cudaGetLastError(), "head_out_kernel launch");
+  ln_silu_head_kernel<<<want < cap ? want : cap, 256, smem, st>>>(x, ldx, g, b, W, bias, out, d_out, rows);
+  return check_launch("ln_silu_head_kernel launch");
 }
 
 int launch_cond(cudaStream_t st, const float* time_table, const int64_t* t, int n_t, const float* class_table,
@@ -228,12 +237,12 @@ int launch_cond(cudaStream_t st, const float* time_table, const int64_t* t, int 
   BG_REQUIRE(B > 0 && (n_t == 1 || n_t == B), "cond: timesteps must have 1 or B entries");
   BG_REQUIRE(class_table == nullptr || label != nullptr, "cond: class table without labels");
   cond_kernel<<<B, 256, 0, st>>>(time_table, t, n_t, class_table, label, cond, B);
-  return check_cuda(cudaGetLastError(), "cond_kernel launch");
+  return check_launch("cond_kernel launch");
 }
 
 int launch_sincos_table(cudaStream_t st, float* out, int n) {
   sincos_table_kernel<<<n, 128, 0, st>>>(out, n);
-  return check_cuda(cudaGetLastError(), "sincos_table_kernel launch");
+  return check_launch("sincos_table_kernel launch");
 }
 
 int launch_cast_f32_to_f16(cudaStream_t st, const float* x, __half* y, size_t n) {
@@ -241,13 +250,13 @@ int launch_cast_f32_to_f16(cudaStream_t st, const float* x, __half* y, size_t n)
   size_t blocks = (n + 255) / 256;
   if (blocks > (size_t)num_sms() * 16) blocks = (size_t)num_sms() * 16;
   cast_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, y, n);
-  return check_cuda(cudaGetLastError(), "cast_kernel launch");
+  return check_launch("cast_kernel launch");
 }
 
 int launch_mask_expand(cudaStream_t st, const uint8_t* face_mask, uint8_t* edge_mask, int BS, int E) {
   const int n = BS * E;
   mask_expand_kernel<<<(n + 255) / 256, 256, 0, st>>>(face_mask, edge_mask, BS, E);
-  return check_cuda(cudaGetLastError(), "mask_expand_kernel launch");
+  return check_launch("mask_expand_kernel launch");
 }
 
 }  // namespace bg

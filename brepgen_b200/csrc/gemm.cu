@@ -33,6 +33,7 @@ struct Cfg {
 
 struct GemmParams {
   int M, N, K;
+  int a_kwrap;   // 0, or the K period of A: A column = k % a_kwrap (K-concatenated weights [W_hi | W_lo] reuse A)
   void* out;
   int ldo;
   int out_f16;
@@ -97,7 +98,8 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           uint8_t* sA = smem + stage * C::STAGE_BYTES;
           uint8_t* sB = sA + C::A_BYTES;
           mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
-          tma_load_2d(sA, &tmA, &full[stage], kb * BK, m_blk * BM);
+          const int ka = p.a_kwrap ? (kb * BK) % p.a_kwrap : kb * BK;
+          tma_load_2d(sA, &tmA, &full[stage], ka, m_blk * BM);
           tma_load_2d(sB, &tmB, &full[stage], kb * BK, n_blk * BN);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -228,7 +230,7 @@ int launch_bn(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB, c
   const int num_tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
   gemm_f16_kernel<BN><<<grid, 256, C::SMEM_BYTES, st>>>(tmA, tmB, p);
-  return check_cuda(cudaGetLastError(), "gemm_f16_kernel launch");
+  return check_launch("gemm_f16_kernel launch");
 }
 
 }  // namespace
@@ -247,10 +249,12 @@ int launch_gemm_f16(cudaStream_t st, const __half* A, int lda, const __half* W, 
   BG_REQUIRE(ep.rowvec == nullptr || (ep.rows_per_vec > 0 && ep.ldv % 4 == 0), "gemm: rowvec");
   const int bn = (N % 256 == 0) ? 256 : 128;
   CUtensorMap tmA, tmB;
-  BG_TRY(make_tmap_2d_f16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM));
+  const int a_cols = ep.a_kwrap > 0 ? ep.a_kwrap : K;
+  BG_REQUIRE(ep.a_kwrap == 0 || (ep.a_kwrap % BK == 0 && K % ep.a_kwrap == 0), "gemm: a_kwrap must divide K");
+  BG_TRY(make_tmap_2d_f16(&tmA, A, (uint64_t)M, (uint64_t)a_cols, (uint64_t)lda, BM));
   BG_TRY(make_tmap_2d_f16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)bn));
   GemmParams p;
-  p.M = M; p.N = N; p.K = K;
+  p.M = M; p.N = N; p.K = K; p.a_kwrap = ep.a_kwrap;
   p.out = ep.out; p.ldo = ep.ldo; p.out_f16 = ep.out_f16; p.relu = ep.relu;
   p.bias = ep.bias; p.resid = ep.resid; p.ldr = ep.ldr;
   p.rowvec = ep.rowvec; p.rows_per_vec = ep.rows_per_vec; p.ldv = ep.ldv;

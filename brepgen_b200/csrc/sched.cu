@@ -117,7 +117,7 @@ int bg_ddpm_step(const float* eps_cond, const float* eps_uncond, float cfg_w, co
   p.w = cfg_w; p.sb = sqrt_one_minus_abar; p.sa = sqrt_abar; p.clip = clip; p.c_x0 = c_x0; p.c_x = c_x; p.sigma = sigma;
   p.seed = seed; p.offset = offset;
   ddpm_step_kernel<<<grid_for((n + 3) / 4), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
-  return check_cuda(cudaGetLastError(), "ddpm_step_kernel launch");
+  return check_launch("ddpm_step_kernel launch");
 }
 
 int bg_pndm_step(const float* x, float* out, int64_t n, float c_sample, float c_eps, const float* e0, float w0,
@@ -128,13 +128,13 @@ int bg_pndm_step(const float* x, float* out, int64_t n, float c_sample, float c_
   p.e[0] = e0; p.e[1] = e1; p.e[2] = e2; p.e[3] = e3;
   p.w[0] = w0; p.w[1] = w1; p.w[2] = w2; p.w[3] = w3;
   pndm_step_kernel<<<grid_for(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
-  return check_cuda(cudaGetLastError(), "pndm_step_kernel launch");
+  return check_launch("pndm_step_kernel launch");
 }
 
 int bg_axpby(const float* x, float a, const float* y, float b, float* out, int64_t n, void* stream) {
   BG_REQUIRE(x && out && n > 0, "axpby: bad arguments");
   axpby_kernel<<<grid_for(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, a, y, b, out, n);
-  return check_cuda(cudaGetLastError(), "axpby_kernel launch");
+  return check_launch("axpby_kernel launch");
 }
 
 }  // extern "C"

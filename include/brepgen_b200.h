@@ -35,6 +35,8 @@ typedef enum {
 
 int bg_version(void);
 const char* bg_last_error(void);
+/* number of CUDA kernels this library has launched so far in this process (bench.py's gpu_launches) */
+uint64_t bg_launch_count(void);
 /* 0 if the current device is sm_100; BG_STATUS_UNSUPPORTED_ARCH otherwise */
 int bg_check_device(void);
 
@@ -53,9 +55,13 @@ typedef struct {
 
 /* Packs the checkpoint (fp16 copies of the GEMM weights, fp32 norms/biases, the 1000-row time-embedding table).
  * `sincos` may be NULL (table built on device) or a device fp32 [1000][768] copy of network.py:1043 sincos_embedding
- * for t = 0..999.  The weights may be freed after the call returns AND `stream` has been synchronised. */
-int bg_denoiser_create(int kind, int use_cf, const BgNamedTensor* weights, int n_weights, const float* sincos,
-                       void* stream, BgDenoiser** out);
+ * for t = 0..999.  The weights may be freed after the call returns AND `stream` has been synchronised.
+ * precision: 0 = plain fp16 tensor-core operands (error ~1e-3 of the fp32 reference, like the reference's own fp16
+ *            autocast path); 1 (default) = in_proj/out_proj weights as fp16 hi+lo pairs and a compensated fc_out tail
+ *            (error ~5e-4); 2 = all four encoder weight matrices as hi+lo pairs.  All modes accumulate in fp32 and keep
+ *            the residual stream, LayerNorm, softmax statistics and the scheduler in fp32. */
+int bg_denoiser_create(int kind, int use_cf, int precision, const BgNamedTensor* weights, int n_weights,
+                       const float* sincos, void* stream, BgDenoiser** out);
 void bg_denoiser_destroy(BgDenoiser* m);
 
 typedef struct {
@@ -92,6 +98,16 @@ int bg_pndm_step(const float* x, float* out, int64_t n, float c_sample, float c_
                  const float* e1, float w1, const float* e2, float w2, const float* e3, float w3, void* stream);
 /* out = a*x + b*y  (y may be NULL); out = eps_cond*(1+w) - eps_uncond*w is bg_axpby(eps_c, 1+w, eps_u, -w) */
 int bg_axpby(const float* x, float a, const float* y, float b, float* out, int64_t n, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Stage glue on the device (replaces the D2H -> numpy loops -> H2D round trips of sample.py:159-183 and :242-261).
+ * Greedy first-seen duplicate removal under max-norm < threshold, also against the corner-swapped box.
+ * ------------------------------------------------------------------------------------------------------------- */
+/* surfPos (B,S,6) -> out_pos (B,S,6): np.round(.,4) survivors packed first, zero padded; out_mask (B,S): 1 = padded */
+int bg_dedup_surfaces(const float* surfPos, int B, int S, float threshold, float* out_pos, uint8_t* out_mask, void* stream);
+/* edgePos (B,S,E,6), surf_mask (B,S) -> edge_mask (B,S,E): 1 = padded face or duplicate edge; slot 0 of a valid face = 0 */
+int bg_dedup_edges(const float* edgePos, const uint8_t* surf_mask, int B, int S, int E, float threshold,
+                   uint8_t* edge_mask, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Unit-level entry points (used by tests and the bench to check/time individual kernels through the C ABI).

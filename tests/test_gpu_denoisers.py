@@ -99,6 +99,26 @@ def test_vs_oracle(kind, use_cf, B, S, E, seed):
     assert err < TOL, err
 
 
+@pytest.mark.parametrize("kind,use_cf,B,S,E,seed", [BIG[0], BIG[6]])
+def test_precision_modes(kind, use_cf, B, S, E, seed):
+    """precision 0 (plain fp16 operands) ~ the reference's own fp16-autocast error; 1 and 2 tighten it."""
+    m, sd = _model(kind, use_cf)
+    inp = _big_inputs(kind, use_cf, B, S, E, seed)
+    with torch.no_grad():
+        ref = O.FORWARDS[kind](sd, *inp.values())
+    mask = inp.get("surf_mask", inp.get("mask"))
+    errs = []
+    for prec in (0, 1, 2):
+        m.precision = prec
+        with torch.no_grad():
+            y = m(*[_cuda(v) for v in inp.values()]).cpu()
+        a, b = (y[~mask], ref[~mask]) if mask is not None else (y, ref)
+        errs.append(rel_l2(a, b))
+    print(f"precision modes {kind}: " + " ".join(f"p{i}={e:.3e}" for i, e in enumerate(errs)))
+    assert errs[0] < 2.5e-3 and errs[1] < TOL and errs[2] < TOL
+    assert errs[2] <= errs[0]
+
+
 def test_forward_is_deterministic_and_repack_on_load():
     m, sd = _model("surfz", False)
     inp = {k: _cuda(v) for k, v in _big_inputs("surfz", False, 2, 40, 0, 4).items()}

@@ -1,0 +1,106 @@
+"""CPU tests: host-side logic of the product package and the structural invariants that pin the scheduler oracle
+(no diffusers golden vectors exist -> 'parity unpinned' for the scheduler arithmetic).
+No compute call of the CUDA library is made here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from brepgen_b200 import _ffi
+from brepgen_b200.models import NETS, reference_sincos_table
+from brepgen_b200.sampler import shard_batch
+from brepgen_b200.schedulers import DDPMScheduler, PNDMScheduler
+from brepgen_b200.spec import denoiser_spec
+from oracle import denoisers as O
+from oracle.schedulers import DDPMOracle, PNDMOracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "brepgen_b200.h")).read()
+    declared = set(re.findall(r"\b(bg_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_ffi.SIGNATURES), declared ^ set(_ffi.SIGNATURES)
+    lib = ctypes.CDLL(_ffi.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _ffi.lib().bg_version() >= 100
+
+
+def test_state_dict_keys_and_load():
+    for kind, cls in NETS.items():
+        for cf in (False, True):
+            m = cls(cf)
+            assert list(m.state_dict().keys()) == [k for k, _ in denoiser_spec(kind, cf)]
+            sd = {k: torch.zeros(s) for k, s in denoiser_spec(kind, cf)}
+            m.load_state_dict(sd)      # strict
+    with pytest.raises(RuntimeError):
+        NETS["surfpos"](False)(torch.zeros(1, 3, 6), torch.tensor([1]), None)   # no CPU path
+
+
+def test_sincos_table_matches_oracle():
+    tab = reference_sincos_table()
+    ref = O.sincos_embedding(torch.arange(1000))
+    assert torch.equal(tab, ref)
+
+
+def test_scheduler_tables_and_coefficients_match_oracle():
+    d, do = DDPMScheduler(clip_sample=True, clip_sample_range=3), DDPMOracle()
+    for n in (1000, 200, 8):
+        d.set_timesteps(n), do.set_timesteps(n)
+        assert torch.equal(d.timesteps, do.timesteps)
+        for t in d.timesteps.tolist()[:: max(1, n // 17)] + [0]:
+            c, co = d.step_coefficients(t), do.coeffs(t)
+            assert np.allclose(c, [float(v) for v in co], rtol=0, atol=0), (t, c, co)
+    p, po = PNDMScheduler(), PNDMOracle()
+    p.set_timesteps(200), po.set_timesteps(200)
+    assert torch.equal(p.timesteps, po.timesteps)
+    # the cross-check the reference itself encodes (sample.py:128-129,144-145): 209 entries, [:158] ends at the 255->250
+    # update so that DDPM(1000)[-250:] resumes at t = 249
+    ts = p.timesteps.tolist()
+    assert len(ts) == 209 and ts[:12] == [995, 992, 992, 990, 990, 987, 987, 985, 985, 982, 982, 980]
+    assert ts[157] == 255 and ts[158] == 250 and ts[-1] == 0
+    d.set_timesteps(1000)
+    assert d.timesteps[-250:].tolist()[0] == 249
+
+
+def test_ddpm_oracle_invariants():
+    o = DDPMOracle()
+    g = torch.Generator().manual_seed(0)
+    x0 = torch.rand(64, generator=g) * 2 - 1
+    eps = torch.randn(64, generator=g)
+    for t in (999, 500, 249, 10, 1):
+        xt = o.add_noise(x0, eps, torch.tensor(t))
+        sb, sa, c0, cx, sig = o.coeffs(t)
+        assert torch.allclose((xt - sb * eps) / sa, x0, atol=2e-4)            # x0 recovery
+        a_prev = o.acp[t - 1]
+        # posterior-mean identity c_x0 + c_x sqrt(abar_t) = sqrt(abar_prev); fp32 tables lose digits in 1 - abar at small t
+        assert abs(float(c0 + cx * sa) - float(a_prev ** 0.5)) < (1e-6 if t >= 249 else 2e-4)
+    assert float(o.acp[0]) == pytest.approx(0.9999, abs=1e-6) and float(o.acp[999]) == pytest.approx(4.036e-5, rel=1e-3)
+    assert o.coeffs(0)[4] == 0
+
+
+def test_pndm_transfer_is_ddim():
+    o = PNDMOracle()
+    g = torch.Generator().manual_seed(1)
+    x0, eps = torch.randn(32, generator=g), torch.randn(32, generator=g)
+    for t, p in ((995, 990), (500, 495), (5, 0)):
+        a_t, a_p = o.acp[t], o.acp[p]
+        xt = a_t ** 0.5 * x0 + (1 - a_t) ** 0.5 * eps
+        ref = a_p ** 0.5 * x0 + (1 - a_p) ** 0.5 * eps
+        assert torch.allclose(o._prev_sample(xt, t, p, eps), ref, atol=5e-4)
+        cs, ce = PNDMScheduler().transfer_coefficients(t, p)
+        assert torch.allclose(cs * xt - ce * eps, ref, atol=5e-4)
+
+
+def test_shard_batch_partitions():
+    for gb in (1, 7, 256, 2048):
+        for ws in (1, 2, 3, 8):
+            spans = [shard_batch(gb, r, ws) for r in range(ws)]
+            assert spans[0][0] == 0 and spans[-1][1] == gb
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
