@@ -250,7 +250,7 @@ int launch_gemm_f16(cudaStream_t st, const __half* A, int lda, const __half* W, 
   const int bn = (N % 256 == 0) ? 256 : 128;
   CUtensorMap tmA, tmB;
   const int a_cols = ep.a_kwrap > 0 ? ep.a_kwrap : K;
-  BG_REQUIRE(ep.a_kwrap == 0 || (ep.a_kwrap % BK == 0 && K % ep.a_kwrap == 0), "gemm: a_kwrap must divide K");
+  BG_REQUIRE(ep.a_kwrap == 0 || (ep.a_kwrap % BK == 0 && ep.a_kwrap <= K), "gemm: a_kwrap must be a multiple of 64");
   BG_TRY(make_tmap_2d_f16(&tmA, A, (uint64_t)M, (uint64_t)a_cols, (uint64_t)lda, BM));
   BG_TRY(make_tmap_2d_f16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)bn));
   GemmParams p;

@@ -25,12 +25,21 @@ def rel_l2(a, b):
 
 def _boxes(g, *shape):
     """random boxes with many near-duplicates, some corner-swapped, some exactly on rounding boundaries"""
-    base = torch.randn(*shape[:-1], 6, generator=g) * 0.3
-    base = torch.round(base * 8) / 8 + 0.02 * torch.randn(*shape[:-1], 6, generator=g)   # clusters ~ threshold apart
-    swap = torch.rand(shape[:-1], generator=g) < 0.2
-    base[swap] = torch.cat([base[swap][..., 3:], base[swap][..., :3]], -1)
+    base = torch.randn(*shape[:-1], 6, generator=g)
+    n = shape[-2]
+    flat = base.view(-1, n, 6)
+    for i in range(1, n):
+        # ~45 % of the slots re-use an earlier slot, perturbed by up to +-0.1 per coordinate (threshold is 0.08, so
+        # both outcomes occur), 30 % of those with the two corners swapped
+        src = torch.randint(0, i, (flat.shape[0],), generator=g)
+        cp = flat[torch.arange(flat.shape[0]), src] + (torch.rand(flat.shape[0], 6, generator=g) - 0.5) * 0.2 \
+            * torch.rand(flat.shape[0], 1, generator=g)
+        sw = torch.rand(flat.shape[0], generator=g) < 0.3
+        cp[sw] = torch.cat([cp[sw][:, 3:], cp[sw][:, :3]], -1)
+        use = torch.rand(flat.shape[0], generator=g) < 0.45
+        flat[use, i] = cp[use]
     edge = torch.rand(shape[:-1], generator=g) < 0.1
-    base[edge] = torch.round(base[edge] * 1e4) / 1e4 + 5e-5
+    base[edge] = torch.round(base[edge] * 1e4) / 1e4 + 5e-5      # values on the np.round(.,4) tie boundary
     return base.float()
 
 
