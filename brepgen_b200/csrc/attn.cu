@@ -11,8 +11,8 @@
 //   warp 4*NT+1     : TMEM allocator + MMA issuer (one elected thread)
 // per key block j and tile t:   S_t = Q_t K_j^T            4 x tcgen05.mma M128 N128 K16  (A,B K-major SW128)
 //                               P_t = exp2(c (S_t - m))     softmax WG: TMEM -> regs -> fp16 -> swizzled smem
-//                               PV_t = P_t V_j              8 x tcgen05.mma M128 N64 K16   (B = V, MN-major SW128)
-//                               O_t = (O_t + PV_{j-1}) * alpha   in registers (fp32)
+//                               O_t (+)= P_t V_j            8 x tcgen05.mma M128 N64 K16   (B = V, MN-major SW128)
+//                               O_t += P_t V_j accumulates in TMEM; lazy rescale of O_t by the softmax WG
 // MMA issue order  QK(0,j) QK(1,j) PV(0,j-1) PV(1,j-1)  lets softmax of block j overlap the PV of block j-1.
 // Fully padded key blocks are skipped through a per-sample block list (result-preserving: their p is exactly 0).
 // Roofline: tensor-bound; 4*L*L*64 flop per (sample, head).
@@ -39,9 +39,12 @@ struct ACfg {
   static constexpr int OFF_V = OFF_K + ST * TILE_BYTES;
   static constexpr int OFF_P = OFF_V + ST * TILE_BYTES;
   static constexpr int OFF_BAR = OFF_P + NT * P_BYTES;
-  static constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
+  static constexpr int OFF_MASKW = OFF_BAR + 512;          // invalid-key bit words: 4 per key block, MAX_KB blocks
+  static constexpr int MAX_KB = 64;                        // L <= 8192
+  static constexpr int SMEM_BYTES = OFF_MASKW + MAX_KB * 16 + 1024;
   static constexpr int TMEM_COLS = (NT == 2) ? 512 : 256;
-  static constexpr int THREADS = NT * 128 + 64;
+  // NT == 2: three full warpgroups (2 softmax + 1 for the producer / MMA warps) so setmaxnreg can move registers
+  static constexpr int THREADS = (NT == 2) ? 384 : NT * 128 + 64;
   static constexpr int TILE_COLS = 192;   // per tile: S at +0 (128 cols), PV at +128 (64 cols)
 };
 
@@ -102,12 +105,29 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
     fence_barrier_init();
   }
   if (warp == MMA_WARP) tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  // invalid-key bit words for every key block this CTA will visit (padded key or key >= L), built once: keeps the
+  // global mask bytes off the per-block critical path
+  uint32_t* maskw = reinterpret_cast<uint32_t*>(smem + C::OFF_MASKW);
+  if (warp < PRODUCER_WARP) {
+    for (int wi = warp; wi < nblk * 4; wi += PRODUCER_WARP) {
+      const int kb = blist ? blist[wi >> 2] : (wi >> 2);
+      const int key = kb * 128 + (wi & 3) * 32 + lane;
+      bool bad = key >= p.L;
+      if (!bad && p.key_mask) bad = p.key_mask[(size_t)b * p.L + key] != 0;
+      const uint32_t w = __ballot_sync(0xffffffffu, bad);
+      if (lane == 0) maskw[wi] = w;
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == PRODUCER_WARP) {
+  // register rebalancing (NT == 2): the softmax warpgroups hold a 128-wide score row per thread; the third warpgroup
+  // (producer, MMA issuer, two idle warps) gives its registers away.  Each role sets its budget inside its own branch.
+  if (warp >= PRODUCER_WARP) {
+   if constexpr (NT == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+   if (warp == PRODUCER_WARP) {
     if (elect_one()) {
       mbar_arrive_expect_tx(q_full, NT * TILE_BYTES);
       for (int t = 0; t < NT; ++t)
@@ -124,7 +144,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
         tma_load_3d(smem + C::OFF_V + s * TILE_BYTES, &tmQKV, &v_full[s], 2 * DMODEL + h * DH, kb * 128, b);
       }
     }
-  } else if (warp == MMA_WARP) {
+   } else if (warp == MMA_WARP) {
     if (elect_one()) {
       constexpr uint32_t idesc_qk = make_idesc_f16(128, 128, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_f16(128, DH, 0, 1);   // B (= V) is MN-major
@@ -156,139 +176,123 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
           const uint32_t v_addr = smem_u32(smem + C::OFF_V + s * TILE_BYTES);
 #pragma unroll
           for (int t = 0; t < NT; ++t) {
-            mbar_wait(&p_full[t], i & 1);
-            mbar_wait(&pv_free[t], (i & 1) ^ 1);
+            mbar_wait(&p_full[t], i & 1);     // P_t(i) written and O_t rescaled (if needed) by the softmax warpgroup
             tc_fence_after();
             const uint32_t p_addr = smem_u32(smem + C::OFF_P + t * P_BYTES);
 #pragma unroll
             for (int k = 0; k < 128 / 16; ++k)
               umma_f16_ss(tmem_base + t * C::TILE_COLS + 128,
                           make_sw128_desc(p_addr + (k >> 2) * (P_BYTES / 2) + (k & 3) * 32),
-                          make_sw128_desc(v_addr + k * 2048), idesc_pv, k > 0 ? 1u : 0u);
+                          make_sw128_desc(v_addr + k * 2048), idesc_pv, (i | k) != 0 ? 1u : 0u);
             umma_commit(&pv_full[t]);
           }
           umma_commit(&v_empty[s]);
         }
       }
     }
+   }
   } else {
+    if constexpr (NT == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     // ------------------------------------------------------------------ softmax warpgroup for query tile t
+    // One thread per query row (== TMEM lane).  The whole 128-key score row lives in registers (one TMEM read, S is
+    // released to the next QK^T right away); O accumulates in TMEM across key blocks and is rescaled lazily: the
+    // exponent reference m_ref only moves when the running max grew by more than 2^8 (p <= 256 is harmless in fp16 P /
+    // fp32 accumulation), so the TMEM read-modify-write of O is rare after the first blocks.
     const int t = warp >> 2;
     const int r = threadIdx.x & 127;                       // query row in tile == TMEM lane
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t s_tmem = tmem_base + lane_base + t * C::TILE_COLS;
-    const uint32_t pv_tmem = s_tmem + 128;
-    uint8_t* sP = smem + C::OFF_P + t * P_BYTES;
+    const uint32_t o_tmem = s_tmem + 128;
+    const uint32_t sP = smem_u32(smem + C::OFF_P + t * P_BYTES) + r * 128;
     const float c = p.scale_log2;
 
-    float m = -INFINITY, l = 0.f;
-    float o[DH];
-#pragma unroll
-    for (int i = 0; i < DH; ++i) o[i] = 0.f;
+    float m_ref = -INFINITY, l = 0.f;
 
     for (int it = 0; it < nblk; ++it) {
-      const int kb = blist ? blist[it] : it;
-      // invalid-key bit masks for the 4 x 32 keys of this block (padded key or beyond L)
-      uint32_t inval[4];
-#pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        const int key = kb * 128 + cc * 32 + lane;
-        bool bad = key >= p.L;
-        if (!bad && p.key_mask) bad = p.key_mask[(size_t)b * p.L + key] != 0;
-        inval[cc] = __ballot_sync(0xffffffffu, bad);
-      }
+      const uint4 iw = *reinterpret_cast<const uint4*>(maskw + it * 4);
+      const uint32_t inval[4] = {iw.x, iw.y, iw.z, iw.w};
 
       mbar_wait(&s_full[t], it & 1);
       tc_fence_after();
+      float s[128];
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) tmem_ld_32x32b_x32(s_tmem + cc * 32, reinterpret_cast<uint32_t*>(s) + cc * 32);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&s_free[t]);          // S_t may be overwritten by QK^T of the next block
 
-      // pass 1: row max
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
-        uint32_t rr[32];
-        tmem_ld_32x32b_x32(s_tmem + cc * 32, rr);
-        tmem_ld_wait();
-        const uint32_t w = inval[cc];
-        if (w == 0) {
+      if ((inval[0] | inval[1] | inval[2] | inval[3]) != 0) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(rr[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, ((w >> i) & 1u) ? -INFINITY : __uint_as_float(rr[i]));
-        }
+        for (int i = 0; i < 128; ++i)
+          if ((inval[i >> 5] >> (i & 31)) & 1u) s[i] = -INFINITY;
       }
-      const float m_new = fmaxf(m, mx);
-      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = ex2((m - m_use) * c);            // m = -inf -> 0
-      const float mc = m_use * c;
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 128; i += 8) {       // four independent FMNMX3 chains
+        mx0 = fmax3(mx0, s[i], s[i + 1]);
+        mx1 = fmax3(mx1, s[i + 2], s[i + 3]);
+        mx2 = fmax3(mx2, s[i + 4], s[i + 5]);
+        mx3 = fmax3(mx3, s[i + 6], s[i + 7]);
+      }
+      const float m_new = fmaxf(fmax3(m_ref, mx0, mx1), fmaxf(mx2, mx3));
 
-      // fold in PV of the previous block (also guarantees the PV MMA no longer reads sP)
-      if (it > 0) {
+      if (it == 0) {
+        m_ref = (m_new == -INFINITY) ? 0.f : m_new;
+      } else {
+        // PV of the previous block done: O_t is complete up to block it-1 and sP is no longer being read
         mbar_wait(&pv_full[t], (it - 1) & 1);
         tc_fence_after();
+        const bool need = (m_new - m_ref) * c > 8.f;
+        if (__any_sync(0xffffffffu, need)) {
+          const float f = need ? ex2((m_ref - m_new) * c) : 1.f;
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          uint32_t rr[32];
-          tmem_ld_32x32b_x32(pv_tmem + hh * 32, rr);
-          tmem_ld_wait();
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t rr[32];
+            tmem_ld_32x32b_x32(o_tmem + hh * 32, rr);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[hh * 32 + i] = (o[hh * 32 + i] + __uint_as_float(rr[i])) * alpha;
+            for (int i = 0; i < 32; ++i) rr[i] = __float_as_uint(__uint_as_float(rr[i]) * f);
+            tmem_st_32x32b_x32(o_tmem + hh * 32, rr);
+          }
+          tmem_st_wait();
+          l *= f;
+          if (need) m_ref = m_new;
         }
-        tc_fence_before();
-        mbar_arrive(&pv_free[t]);
       }
+      const float2 c2 = make_float2(c, c);
+      const float2 nmc2 = make_float2(-m_ref * c, -m_ref * c);
 
-      // pass 2: p = exp2(c s - c m), row sum, fp16 P into the K-major SW128 layout
-      float rowsum = 0.f;
-#pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
-        uint32_t rr[32];
-        tmem_ld_32x32b_x32(s_tmem + cc * 32, rr);
-        tmem_ld_wait();
-        const uint32_t w = inval[cc];
-        float pr[32];
+      // p = exp2(c s - c m_ref), row sum (packed f32x2 math), fp16 P into the K-major SW128 layout
+      float2 acc = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float e = ex2(fmaf(__uint_as_float(rr[i]), c, -mc));
-          if (w != 0 && ((w >> i) & 1u)) e = 0.f;
-          pr[i] = e;
-          rowsum += e;
-        }
+      for (int j8 = 0; j8 < 16; ++j8) {                      // 16-byte chunk (8 keys) index along the 128 keys
+        uint32_t pk[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const int j8 = cc * 4 + q;                       // 16-byte chunk index along the 128 keys
-          __half2 h0 = __floats2half2_rn(pr[8 * q], pr[8 * q + 1]);
-          __half2 h1 = __floats2half2_rn(pr[8 * q + 2], pr[8 * q + 3]);
-          __half2 h2 = __floats2half2_rn(pr[8 * q + 4], pr[8 * q + 5]);
-          __half2 h3 = __floats2half2_rn(pr[8 * q + 6], pr[8 * q + 7]);
-          uint4 u;
-          u.x = *reinterpret_cast<uint32_t*>(&h0);
-          u.y = *reinterpret_cast<uint32_t*>(&h1);
-          u.z = *reinterpret_cast<uint32_t*>(&h2);
-          u.w = *reinterpret_cast<uint32_t*>(&h3);
-          uint8_t* dst = sP + (j8 >> 3) * (P_BYTES / 2) + r * 128 + (((j8 & 7) ^ (r & 7)) << 4);
-          *reinterpret_cast<uint4*>(dst) = u;
+          const float2 a = ffma2(make_float2(s[8 * j8 + 2 * q], s[8 * j8 + 2 * q + 1]), c2, nmc2);
+          const float2 e = make_float2(ex2(a.x), ex2(a.y));
+          if (q & 1) acc1 = fadd2(acc1, e); else acc = fadd2(acc, e);
+          __half2 h = __floats2half2_rn(e.x, e.y);
+          pk[q] = *reinterpret_cast<uint32_t*>(&h);
         }
+        st_shared_v4(sP + (j8 >> 3) * (P_BYTES / 2) + (((j8 & 7) ^ (r & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
       }
-      tc_fence_before();
-      mbar_arrive(&s_free[t]);          // S_t may be overwritten by QK of the next block
+      tc_fence_before();                // orders the (rare) O rescale before the PV MMA that p_full releases
       fence_proxy_async_smem();         // generic-proxy writes of P -> visible to the tensor core (async proxy)
       mbar_arrive(&p_full[t]);
-      l = l * alpha + rowsum;
-      m = m_new;
+      l += (acc.x + acc.y) + (acc1.x + acc1.y);
     }
 
+    float o[DH];
     if (nblk > 0) {
       mbar_wait(&pv_full[t], (nblk - 1) & 1);
       tc_fence_after();
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        uint32_t rr[32];
-        tmem_ld_32x32b_x32(pv_tmem + hh * 32, rr);
-        tmem_ld_wait();
+      for (int hh = 0; hh < 2; ++hh) tmem_ld_32x32b_x32(o_tmem + hh * 32, reinterpret_cast<uint32_t*>(o) + hh * 32);
+      tmem_ld_wait();
+    } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[hh * 32 + i] += __uint_as_float(rr[i]);
-      }
+      for (int i = 0; i < DH; ++i) o[i] = 0.f;
     }
     const int row = (qgrp * NT + t) * 128 + r;
     if (row < p.L) {
@@ -358,6 +362,7 @@ int launch_nt(cudaStream_t st, const CUtensorMap& tm, const AttnParams& p) {
 int launch_attention(cudaStream_t st, const AttnArgs& a) {
   BG_REQUIRE(a.qkv && a.out && a.B > 0 && a.L > 0, "attention: bad arguments");
   BG_REQUIRE(a.ldo % 8 == 0, "attention: output pitch must be a multiple of 8");
+  BG_REQUIRE(a.L <= 128 * ACfg<2>::MAX_KB, "attention: sequence longer than 8192 tokens is not supported");
   BG_REQUIRE((a.blk_list == nullptr) == (a.blk_count == nullptr), "attention: blk_list and blk_count go together");
   CUtensorMap tm;
   BG_TRY(make_tmap_3d_f16(&tm, a.qkv, (uint64_t)a.B, (uint64_t)a.L, 3 * DMODEL, 3 * DMODEL, 128));
