@@ -9,7 +9,7 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbrepgen_b200.so")
+LIB_PATH = os.environ.get("BG_LIB", os.path.join(_HERE, "libbrepgen_b200.so"))   # BG_LIB: debug builds only
 
 vp, i32, i64, u64, f32, sz = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float, C.c_size_t
 

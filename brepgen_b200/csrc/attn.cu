@@ -17,9 +17,15 @@
 // Fully padded key blocks are skipped through a per-sample block list (result-preserving: their p is exactly 0).
 // Roofline: tensor-bound; 4*L*L*64 flop per (sample, head).
 #include <math.h>
+#include <stdlib.h>
 
 #include "bg_internal.h"
 #include "ptx.cuh"
+
+#ifdef BG_ATTN_TRACE
+__device__ long long g_trace[2][32][8];
+extern "C" int bg_debug_read_trace(long long* host) { return (int)cudaMemcpyFromSymbol(host, g_trace, sizeof(g_trace)); }
+#endif
 
 namespace bg {
 
@@ -33,12 +39,13 @@ constexpr int P_BYTES = 128 * 128 * 2;     // 32 KB: two K-major SW128 blocks of
 
 template <int NT>
 struct ACfg {
-  static constexpr int ST = (NT == 2) ? 3 : 2;
+  static constexpr int ST = (NT == 2) ? 3 : 2;              // K / V ring depth
+  static constexpr int PB = 1;                              // P buffers per tile
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_K = NT * TILE_BYTES;
   static constexpr int OFF_V = OFF_K + ST * TILE_BYTES;
   static constexpr int OFF_P = OFF_V + ST * TILE_BYTES;
-  static constexpr int OFF_BAR = OFF_P + NT * P_BYTES;
+  static constexpr int OFF_BAR = OFF_P + NT * PB * P_BYTES;
   static constexpr int OFF_MASKW = OFF_BAR + 512;          // invalid-key bit words: 4 per key block, MAX_KB blocks
   static constexpr int MAX_KB = 64;                        // L <= 8192
   static constexpr int SMEM_BYTES = OFF_MASKW + MAX_KB * 16 + 1024;
@@ -58,7 +65,9 @@ struct AttnParams {
   float scale_log2;   // log2(e) / sqrt(64)
 };
 
-template <int NT>
+// PM: 4-bit mask over the 4 element pairs of each 8-key chunk whose exp2 runs as a polynomial on the FMA pipe instead of
+// MUFU.EX2 (the XU pipe, 16 ex2/clk/SM, is the binding unit of d=64 attention on B200)
+template <int NT, int PM>
 __global__ void __launch_bounds__(ACfg<NT>::THREADS, (NT == 2) ? 1 : 2)
 attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   using C = ACfg<NT>;
@@ -74,8 +83,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   uint64_t* s_free = s_full + NT;
   uint64_t* p_full = s_free + NT;
   uint64_t* pv_full = p_full + NT;
-  uint64_t* pv_free = pv_full + NT;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_free + NT);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_full + NT * C::PB);   // pv_full[t * PB + (block % PB)]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -91,16 +99,15 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
     mbar_init(q_full, 1);
     for (int i = 0; i < C::ST; ++i) {
       mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
+      mbar_init(&k_empty[i], NT);     // one tcgen05.commit per MMA-issuing thread (one thread per query tile)
       mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 1);
+      mbar_init(&v_empty[i], NT);
     }
     for (int t = 0; t < NT; ++t) {
       mbar_init(&s_full[t], 1);
       mbar_init(&s_free[t], 128);
       mbar_init(&p_full[t], 128);
-      mbar_init(&pv_full[t], 1);
-      mbar_init(&pv_free[t], 128);
+      for (int i = 0; i < C::PB; ++i) mbar_init(&pv_full[t * C::PB + i], 1);
     }
     fence_barrier_init();
   }
@@ -144,8 +151,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
         tma_load_3d(smem + C::OFF_V + s * TILE_BYTES, &tmQKV, &v_full[s], 2 * DMODEL + h * DH, kb * 128, b);
       }
     }
-   } else if (warp == MMA_WARP) {
+   } else if (warp < MMA_WARP + NT) {
+    // one MMA-issuing thread per query tile: the two softmax warpgroups are not coupled through one in-order issuer
     if (elect_one()) {
+      const int t = warp - MMA_WARP;
       constexpr uint32_t idesc_qk = make_idesc_f16(128, 128, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_f16(128, DH, 0, 1);   // B (= V) is MN-major
       mbar_wait(q_full, 0);
@@ -154,38 +163,31 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
         if (it < nblk) {
           const int s = it % C::ST;
           mbar_wait(&k_full[s], (it / C::ST) & 1);
+          mbar_wait(&s_free[t], (it & 1) ^ 1);
           tc_fence_after();
           const uint32_t k_addr = smem_u32(smem + C::OFF_K + s * TILE_BYTES);
+          const uint32_t q_addr = smem_u32(smem + C::OFF_Q + t * TILE_BYTES);
 #pragma unroll
-          for (int t = 0; t < NT; ++t) {
-            mbar_wait(&s_free[t], (it & 1) ^ 1);
-            tc_fence_after();
-            const uint32_t q_addr = smem_u32(smem + C::OFF_Q + t * TILE_BYTES);
-#pragma unroll
-            for (int k = 0; k < DH / 16; ++k)
-              umma_f16_ss(tmem_base + t * C::TILE_COLS, make_sw128_desc(q_addr + k * 32), make_sw128_desc(k_addr + k * 32),
-                          idesc_qk, k > 0 ? 1u : 0u);
-            umma_commit(&s_full[t]);
-          }
+          for (int k = 0; k < DH / 16; ++k)
+            umma_f16_ss(tmem_base + t * C::TILE_COLS, make_sw128_desc(q_addr + k * 32), make_sw128_desc(k_addr + k * 32),
+                        idesc_qk, k > 0 ? 1u : 0u);
+          umma_commit(&s_full[t]);
           umma_commit(&k_empty[s]);
         }
         if (it > 0) {
           const int i = it - 1;
           const int s = i % C::ST;
           mbar_wait(&v_full[s], (i / C::ST) & 1);
+          mbar_wait(&p_full[t], i & 1);       // P_t(i) written and O_t rescaled (if needed) by the softmax warpgroup
+          tc_fence_after();
           const uint32_t v_addr = smem_u32(smem + C::OFF_V + s * TILE_BYTES);
+          const uint32_t p_addr = smem_u32(smem + C::OFF_P + (t * C::PB + i % C::PB) * P_BYTES);
 #pragma unroll
-          for (int t = 0; t < NT; ++t) {
-            mbar_wait(&p_full[t], i & 1);     // P_t(i) written and O_t rescaled (if needed) by the softmax warpgroup
-            tc_fence_after();
-            const uint32_t p_addr = smem_u32(smem + C::OFF_P + t * P_BYTES);
-#pragma unroll
-            for (int k = 0; k < 128 / 16; ++k)
-              umma_f16_ss(tmem_base + t * C::TILE_COLS + 128,
-                          make_sw128_desc(p_addr + (k >> 2) * (P_BYTES / 2) + (k & 3) * 32),
-                          make_sw128_desc(v_addr + k * 2048), idesc_pv, (i | k) != 0 ? 1u : 0u);
-            umma_commit(&pv_full[t]);
-          }
+          for (int k = 0; k < 128 / 16; ++k)
+            umma_f16_ss(tmem_base + t * C::TILE_COLS + 128,
+                        make_sw128_desc(p_addr + (k >> 2) * (P_BYTES / 2) + (k & 3) * 32),
+                        make_sw128_desc(v_addr + k * 2048), idesc_pv, (i | k) != 0 ? 1u : 0u);
+          umma_commit(&pv_full[t * C::PB + i % C::PB]);
           umma_commit(&v_empty[s]);
         }
       }
@@ -203,23 +205,41 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t s_tmem = tmem_base + lane_base + t * C::TILE_COLS;
     const uint32_t o_tmem = s_tmem + 128;
-    const uint32_t sP = smem_u32(smem + C::OFF_P + t * P_BYTES) + r * 128;
+    const uint32_t sP0 = smem_u32(smem + C::OFF_P + t * C::PB * P_BYTES) + r * 128;
+    // PV(i) reads P buffer i % PB and completes on pv_full[t][i % PB] (its (i / PB)-th completion)
+    auto wait_pv = [&](int i) { mbar_wait(&pv_full[t * C::PB + i % C::PB], (i / C::PB) & 1); };
     const float c = p.scale_log2;
 
     float m_ref = -INFINITY, l = 0.f;
+
+    // Ping-pong of the two softmax warpgroups over the XU (MUFU.EX2) pipe, which is the binding unit: warpgroup t runs
+    // its exponential phase only while holding the token (named barrier 1 + t); meanwhile the other warpgroup does its
+    // TMEM load / row max / fences.  Without this both warpgroups run in lock-step and fight for the XU pipe.
+    if (NT == 2 && t == 1 && nblk > 0) named_bar_arrive(1, 256);
 
     for (int it = 0; it < nblk; ++it) {
       const uint4 iw = *reinterpret_cast<const uint4*>(maskw + it * 4);
       const uint32_t inval[4] = {iw.x, iw.y, iw.z, iw.w};
 
+#ifdef BG_ATTN_TRACE
+      long long tr[8];
+      const bool trace = blockIdx.x == 3 && blockIdx.y == 5 && blockIdx.z == 2 && (threadIdx.x & 127) == 0 && it < 32;
+      tr[0] = clock64();
+#endif
       mbar_wait(&s_full[t], it & 1);
       tc_fence_after();
+#ifdef BG_ATTN_TRACE
+      tr[1] = clock64();
+#endif
       float s[128];
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) tmem_ld_32x32b_x32(s_tmem + cc * 32, reinterpret_cast<uint32_t*>(s) + cc * 32);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&s_free[t]);          // S_t may be overwritten by QK^T of the next block
+#ifdef BG_ATTN_TRACE
+      tr[2] = clock64();
+#endif
 
       if ((inval[0] | inval[1] | inval[2] | inval[3]) != 0) {
 #pragma unroll
@@ -239,11 +259,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
       if (it == 0) {
         m_ref = (m_new == -INFINITY) ? 0.f : m_new;
       } else {
-        // PV of the previous block done: O_t is complete up to block it-1 and sP is no longer being read
-        mbar_wait(&pv_full[t], (it - 1) & 1);
-        tc_fence_after();
         const bool need = (m_new - m_ref) * c > 8.f;
         if (__any_sync(0xffffffffu, need)) {
+          wait_pv(it - 1);                // O_t complete up to block it-1 before its read-modify-write
+          tc_fence_after();
           const float f = need ? ex2((m_ref - m_new) * c) : 1.f;
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
@@ -259,6 +278,18 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
           if (need) m_ref = m_new;
         }
       }
+#ifdef BG_ATTN_TRACE
+      tr[3] = clock64();
+#endif
+      if (it >= C::PB) wait_pv(it - C::PB);   // the PV MMA that read this P buffer has finished
+#ifdef BG_ATTN_TRACE
+      tr[4] = clock64();
+#endif
+      if (NT == 2) named_bar_sync(1 + t, 256);
+#ifdef BG_ATTN_TRACE
+      tr[5] = clock64();
+#endif
+      const uint32_t sP = sP0 + (it % C::PB) * P_BYTES;
       const float2 c2 = make_float2(c, c);
       const float2 nmc2 = make_float2(-m_ref * c, -m_ref * c);
 
@@ -270,22 +301,31 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float2 a = ffma2(make_float2(s[8 * j8 + 2 * q], s[8 * j8 + 2 * q + 1]), c2, nmc2);
-          const float2 e = make_float2(ex2(a.x), ex2(a.y));
+          const float2 e = ((PM >> q) & 1) ? exp2_poly2(a) : make_float2(ex2(a.x), ex2(a.y));
           if (q & 1) acc1 = fadd2(acc1, e); else acc = fadd2(acc, e);
           __half2 h = __floats2half2_rn(e.x, e.y);
           pk[q] = *reinterpret_cast<uint32_t*>(&h);
         }
         st_shared_v4(sP + (j8 >> 3) * (P_BYTES / 2) + (((j8 & 7) ^ (r & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
       }
+#ifdef BG_ATTN_TRACE
+      tr[6] = clock64();
+#endif
+      if (NT == 2 && !(t == 1 && it == nblk - 1)) named_bar_arrive(1 + (1 - t), 256);   // hand the XU token over
       tc_fence_before();                // orders the (rare) O rescale before the PV MMA that p_full releases
       fence_proxy_async_smem();         // generic-proxy writes of P -> visible to the tensor core (async proxy)
       mbar_arrive(&p_full[t]);
+#ifdef BG_ATTN_TRACE
+      tr[7] = clock64();
+      if (trace)
+        for (int q = 0; q < 8; ++q) g_trace[t][it][q] = tr[q];
+#endif
       l += (acc.x + acc.y) + (acc1.x + acc1.y);
     }
 
     float o[DH];
     if (nblk > 0) {
-      mbar_wait(&pv_full[t], (nblk - 1) & 1);
+      wait_pv(nblk - 1);
       tc_fence_after();
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) tmem_ld_32x32b_x32(o_tmem + hh * 32, reinterpret_cast<uint32_t*>(o) + hh * 32);
@@ -343,17 +383,17 @@ __global__ void block_list_kernel(const uint8_t* __restrict__ key_mask, int L, i
   }
 }
 
-template <int NT>
+template <int NT, int PM>
 int launch_nt(cudaStream_t st, const CUtensorMap& tm, const AttnParams& p) {
   using C = ACfg<NT>;
   static bool configured = false;
   if (!configured) {
-    BG_CUDA(cudaFuncSetAttribute(attn_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    BG_CUDA(cudaFuncSetAttribute(attn_kernel<NT, PM>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     configured = true;
   }
   const int nq = (p.L + 127) / 128;
   dim3 grid((nq + NT - 1) / NT, NHEAD, p.B);
-  attn_kernel<NT><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(tm, p);
+  attn_kernel<NT, PM><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(tm, p);
   return check_launch("attn_kernel launch");
 }
 
@@ -370,7 +410,15 @@ int launch_attention(cudaStream_t st, const AttnArgs& a) {
   p.out = a.out; p.ldo = a.ldo; p.B = a.B; p.L = a.L; p.nkb = (a.L + 127) / 128;
   p.key_mask = a.key_mask; p.blk_list = a.blk_list; p.blk_count = a.blk_count;
   p.scale_log2 = 1.4426950408889634f / 8.0f;
-  return (a.L > 128) ? launch_nt<2>(st, tm, p) : launch_nt<1>(st, tm, p);
+  if (a.L <= 128) return launch_nt<1, 0>(st, tm, p);
+  static int poly = -1;                 // BG_ATTN_POLY = 0 | 1 (25 % of the exponentials) | 2 (50 %); tuning knob
+  if (poly < 0) {
+    const char* e = getenv("BG_ATTN_POLY");
+    poly = e ? atoi(e) : 1;
+  }
+  if (poly == 0) return launch_nt<2, 0x0>(st, tm, p);
+  if (poly == 2) return launch_nt<2, 0xA>(st, tm, p);
+  return launch_nt<2, 0x8>(st, tm, p);
 }
 
 int launch_build_block_list(cudaStream_t st, const uint8_t* key_mask, int B, int L, int* blk_list, int* blk_count) {

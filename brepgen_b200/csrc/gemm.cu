@@ -4,11 +4,12 @@
 // nn.TransformerEncoderLayer / the embed MLPs, /root/reference/network.py:1076-1099) and of the VAE convs
 // (after im2col).  nn.Linear stores W as [N][K] row-major == K-major B operand, so weights are used as packed.
 //
-// Structure (one persistent CTA per SM, 256 threads):
+// Structure (one persistent CTA per SM, 384 threads):
 //   warp 0  : TMA producer  (A tile 128x64, W tile BNx64, SWIZZLE_128B, STAGES-deep mbarrier ring)
 //   warp 1  : MMA issuer    (one elected thread: 4 x tcgen05.mma.kind::f16 M128 N=BN K16 per 64-wide k-block)
 //   warp 2  : TMEM allocator (2 x BN fp32 columns: accumulator double buffer -> epilogue overlaps next tile)
-//   warps 4-7: epilogue     (tcgen05.ld 32x32b, bias / row-vector / residual / ReLU, fp16 or fp32 store)
+//   warps 4-11: epilogue    (8 warps: TMEM lane quarter = warp % 4, column half = (warp - 4) / 4; tcgen05.ld 32x32b,
+//                            residual / row-vector loads issued BEFORE the TMEM wait so their latency overlaps it)
 // Roofline: tensor-bound; 2*M*N*K flop per launch.
 #include "bg_internal.h"
 #include "ptx.cuh"
@@ -47,7 +48,7 @@ struct GemmParams {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -72,7 +73,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 128);
+      mbar_init(&tempty[i], 256);
     }
     fence_barrier_init();
   }
@@ -135,52 +136,64 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else if (warp >= 4) {
-    const int ew = warp - 4;
+    const int ew = (warp - 4) & 3;            // TMEM lane quarter this warp may access
+    const int half = (warp - 4) >> 2;         // column half of the tile
     const int row_in_tile = ew * 32 + lane;
+    constexpr int CHUNKS = BN / 64;           // 32-column chunks per half
     int acc = 0;
     uint32_t accphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
-      mbar_wait(&tfull[acc], accphase);
-      tc_fence_after();
       const int row = m_blk * BM + row_in_tile;
       const bool row_ok = row < p.M;
       const float* vec = p.rowvec ? p.rowvec + (size_t)(row_ok ? row / p.rows_per_vec : 0) * p.ldv : nullptr;
       const float* res = p.resid ? p.resid + (size_t)(row_ok ? row : 0) * p.ldr : nullptr;
+      const int colbase = n_blk * BN + half * (BN / 2);
+      // additive terms of the first chunk are fetched before waiting for the accumulator
+      float add[32];
+      auto fetch_add = [&](int col0) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) add[i] = 0.f;
+        if (!row_ok) return;
+        if (res) {
+          const float4* rp = reinterpret_cast<const float4*>(res + col0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 t = rp[i];
+            add[4 * i] = t.x; add[4 * i + 1] = t.y; add[4 * i + 2] = t.z; add[4 * i + 3] = t.w;
+          }
+        }
+        if (vec) {
+          const float4* vp = reinterpret_cast<const float4*>(vec + col0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 t = __ldg(vp + i);
+            add[4 * i] += t.x; add[4 * i + 1] += t.y; add[4 * i + 2] += t.z; add[4 * i + 3] += t.w;
+          }
+        }
+        if (p.bias) {
+          const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 t = __ldg(bp + i);
+            add[4 * i] += t.x; add[4 * i + 1] += t.y; add[4 * i + 2] += t.z; add[4 * i + 3] += t.w;
+          }
+        }
+      };
+      fetch_add(colbase);
+      mbar_wait(&tfull[acc], accphase);
+      tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = 0; c < CHUNKS; ++c) {
         uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN + c * 32, r);
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN + half * (BN / 2) + c * 32, r);
         tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + add[i];
+        const int col0 = colbase + c * 32;
+        if (c + 1 < CHUNKS) fetch_add(col0 + 32);     // next chunk's loads are in flight while this one is stored
         if (row_ok) {
-          const int col0 = n_blk * BN + c * 32;
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-          if (p.bias) {
-            const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float4 t = __ldg(bp + i);
-              v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
-            }
-          }
-          if (vec) {
-            const float4* vp = reinterpret_cast<const float4*>(vec + col0);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float4 t = __ldg(vp + i);
-              v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
-            }
-          }
-          if (res) {
-            const float4* rp = reinterpret_cast<const float4*>(res + col0);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float4 t = rp[i];
-              v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
-            }
-          }
           if (p.relu) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
@@ -229,7 +242,7 @@ int launch_bn(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB, c
   }
   const int num_tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  gemm_f16_kernel<BN><<<grid, 256, C::SMEM_BYTES, st>>>(tmA, tmB, p);
+  gemm_f16_kernel<BN><<<grid, 384, C::SMEM_BYTES, st>>>(tmA, tmB, p);
   return check_launch("gemm_f16_kernel launch");
 }
 

@@ -58,6 +58,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// named barriers (id 1..15; id 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // ---------------------------------------------------------------- fences
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -188,6 +196,24 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
   return d;
+}
+
+// exp2 of two values on the FMA pipe: round-to-nearest split x = n + f (magic-number add), degree-4 polynomial for
+// 2^f on [-0.5, 0.5] (max rel. error 3e-6, far below the fp16 rounding of P), exponent add through the float bits.
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -125.f);
+  x.y = fmaxf(x.y, -125.f);
+  const float2 t = fadd2(x, make_float2(12582912.f, 12582912.f));
+  const float2 n = fadd2(t, make_float2(-12582912.f, -12582912.f));
+  const float2 f = ffma2(n, make_float2(-1.f, -1.f), x);
+  float2 q = ffma2(f, make_float2(0.00960039534f, 0.00960039534f), make_float2(0.0559168942f, 0.0559168942f));
+  q = ffma2(q, f, make_float2(0.240237191f, 0.240237191f));
+  q = ffma2(q, f, make_float2(0.69312197f, 0.69312197f));
+  q = ffma2(q, f, make_float2(1.f, 1.f));
+  float2 r;
+  r.x = __int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23));
+  r.y = __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23));
+  return r;
 }
 
 __device__ __forceinline__ float ex2(float x) {
