@@ -1,0 +1,679 @@
+// Surface (2-D) and edge (1-D) VAE decoders: latents -> 32x32 / 32-point control grids.
+//
+// Reference: AutoencoderKLFastDecode.forward /root/reference/network.py:1013-1040 (diffusers 0.27 `Decoder`, cfg
+// sample.py:72-82) and AutoencoderKL1DFastDecode.forward network.py:846-858 (Decoder1D :188-299, UNetMidBlock1D :51-83,
+// UpBlock1D :30-48, cfg sample.py:86-97); layer-by-layer arithmetic: SURVEY.md Appendix A.1 / A.2.
+//
+// Layout: activations are channels-last ([sample][position][channel]), fp32 for the residual stream and fp16 for GEMM
+// operands.  Every convolution is an im2col gather (fp16, nearest-2x upsampling folded into the gather) followed by the
+// tcgen05 GEMM of gemm.cu, whose epilogue adds bias and the residual; GroupNorm + SiLU/GELU (+ residual) is one
+// CTA-per-sample kernel; the tiny attentions (16 tokens x 512 / 4 tokens x 16 heads x 32) run on CUDA cores.
+// Decode is ~0.13 % of the cascade's FLOPs, so the explicit im2col (HBM-bound, ~9x activation traffic) is
+// accepted here; the GEMMs are tensor-bound.
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/brepgen_b200.h"
+#include "bg_internal.h"
+
+namespace bg {
+namespace {
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+inline int round64(int k) { return (k + 63) / 64 * 64; }
+
+// ------------------------------------------------------------------------------------------------ kernels
+// weights [Cout][Cin][taps] fp32 -> [Cout_pad][Kpad] fp16 with k = tap * Cin + cin (zero padded)
+__global__ void pack_conv_kernel(const float* __restrict__ w, __half* __restrict__ dst, int Cout, int Cin, int taps, int Kpad,
+                                 int Cout_pad) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)Cout_pad * Kpad) return;
+  const int co = (int)(i / Kpad), k = (int)(i % Kpad);
+  float v = 0.f;
+  if (co < Cout && k < taps * Cin) {
+    const int tap = k / Cin, ci = k % Cin;
+    v = w[((size_t)co * Cin + ci) * taps + tap];
+  }
+  dst[i] = __float2half_rn(v);
+}
+
+// z (N, 3, P) fp32 -> y (N, P, 3) fp16, y = W z + b  (post_quant_conv, 1x1)
+__global__ void postquant_kernel(const float* __restrict__ z, const float* __restrict__ w, const float* __restrict__ b,
+                                 __half* __restrict__ y, int N, int P) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * P) return;
+  const int n = i / P, p = i % P;
+  const float z0 = z[((size_t)n * 3 + 0) * P + p], z1 = z[((size_t)n * 3 + 1) * P + p], z2 = z[((size_t)n * 3 + 2) * P + p];
+#pragma unroll
+  for (int co = 0; co < 3; ++co)
+    y[(size_t)i * 3 + co] = __float2half_rn(b[co] + w[co * 3] * z0 + w[co * 3 + 1] * z1 + w[co * 3 + 2] * z2);
+}
+
+// in (N, H, W, C) fp16 -> A (N*Ho*Wo, Kpad) fp16, 3x3 pad 1 on the (optionally nearest-2x upsampled) image
+__global__ void im2col2d_kernel(const __half* __restrict__ in, __half* __restrict__ A, int H, int W, int C, int up, int Kpad,
+                                size_t total_vec, int vec) {
+  const int Ho = H * up, Wo = W * up;
+  const int kvec = Kpad / vec;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = i / kvec;
+    const int k = (int)(i % kvec) * vec;
+    const int x = (int)(row % Wo), y = (int)((row / Wo) % Ho);
+    const size_t n = row / ((size_t)Wo * Ho);
+    __half* dst = A + row * Kpad + k;
+    if (vec == 8) {
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (k < 9 * C) {
+        const int tap = k / C, c = k % C;
+        const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+        if (yy >= 0 && yy < Ho && xx >= 0 && xx < Wo)
+          v = *reinterpret_cast<const uint4*>(in + ((n * H + yy / up) * W + xx / up) * C + c);
+      }
+      *reinterpret_cast<uint4*>(dst) = v;
+    } else {
+      __half v = __float2half_rn(0.f);
+      if (k < 9 * C) {
+        const int tap = k / C, c = k % C;
+        const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+        if (yy >= 0 && yy < Ho && xx >= 0 && xx < Wo) v = in[((n * H + yy / up) * W + xx / up) * C + c];
+      }
+      *dst = v;
+    }
+  }
+}
+
+// in (N, L, C) fp16 -> A (N*L, Kpad) fp16, kernel size ks (odd), pad ks/2
+__global__ void im2col1d_kernel(const __half* __restrict__ in, __half* __restrict__ A, int L, int C, int ks, int Kpad,
+                                size_t total_vec, int vec) {
+  const int kvec = Kpad / vec;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = i / kvec;
+    const int k = (int)(i % kvec) * vec;
+    const int l = (int)(row % L);
+    const size_t n = row / L;
+    __half* dst = A + row * Kpad + k;
+    if (vec == 8) {
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (k < ks * C) {
+        const int tap = k / C, c = k % C;
+        const int ll = l + tap - ks / 2;
+        if (ll >= 0 && ll < L) v = *reinterpret_cast<const uint4*>(in + (n * L + ll) * C + c);
+      }
+      *reinterpret_cast<uint4*>(dst) = v;
+    } else {
+      __half v = __float2half_rn(0.f);
+      if (k < ks * C) {
+        const int tap = k / C, c = k % C;
+        const int ll = l + tap - ks / 2;
+        if (ll >= 0 && ll < L) v = in[(n * L + ll) * C + c];
+      }
+      *dst = v;
+    }
+  }
+}
+
+__device__ __forceinline__ float act_fn(float y, int act) {
+  if (act == 1) return y / (1.f + __expf(-y));                       // SiLU
+  if (act == 2) return 0.5f * y * (1.f + erff(y * 0.70710678118f));   // exact (erf) GELU
+  return y;
+}
+
+// GroupNorm over (P positions x C/G channels) per sample and group, then activation, then optional residual add.
+// x (N, P, C) fp32 (pitch ldx per position); one CTA per sample, blockDim == C, thread <-> channel.
+__global__ void groupnorm_kernel(const float* __restrict__ x, int ldx, int P, int C, int G, float eps,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta, int act,
+                                 const float* __restrict__ resid, float* __restrict__ out32, __half* __restrict__ out16) {
+  __shared__ float s_part[32];
+  __shared__ float s_stat[64];     // mean[G], rstd[G]
+  const int n = blockIdx.x, c = threadIdx.x;
+  const int cpg = C / G;
+  const int g = c / cpg;
+  const float* xs = x + (size_t)n * P * ldx;
+  const int lane = c & 31, warp = c >> 5, nwarp = blockDim.x >> 5;
+  const float cnt = (float)P * cpg;
+
+  auto group_reduce = [&](float v) -> float {      // sum of v over all threads of this thread's group
+    if (cpg <= 32) {
+      for (int o = cpg >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      return v;
+    }
+    // G == 1 (or groups spanning several warps with G small): block-wide reduction, groups are warp aligned
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if (lane == 0) s_part[warp] = v;
+    __syncthreads();
+    const int wpg = cpg >> 5;                      // warps per group
+    float t = 0.f;
+    const int w0 = (warp / wpg) * wpg;
+    for (int w = 0; w < wpg; ++w) t += s_part[w0 + w];
+    return t;
+  };
+  (void)nwarp;
+
+  float s = 0.f;
+  for (int p = 0; p < P; ++p) s += xs[(size_t)p * ldx + c];
+  const float mean = group_reduce(s) / cnt;
+  float q = 0.f;
+  for (int p = 0; p < P; ++p) {
+    const float d = xs[(size_t)p * ldx + c] - mean;
+    q += d * d;
+  }
+  const float rstd = rsqrtf(group_reduce(q) / cnt + eps);
+  (void)s_stat;
+  const float ga = gamma[c] * rstd, be = beta[c] - mean * gamma[c] * rstd;
+  for (int p = 0; p < P; ++p) {
+    float y = act_fn(xs[(size_t)p * ldx + c] * ga + be, act);
+    const size_t o = ((size_t)n * P + p) * C + c;
+    if (resid) y += resid[o];
+    if (out32) out32[o] = y;
+    if (out16) out16[o] = __float2half_rn(y);
+  }
+}
+
+// small multi-head attention: qkv (N*T, 3*C) fp16 [q | k | v], out (N*T, C) fp16; heads Hh x dh = C; T*T*Hh <= 256
+__global__ void __launch_bounds__(256) small_attention_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int T,
+                                                              int Hh, int dh, float scale) {
+  extern __shared__ float sm[];          // q,k,v: 3 * T * C floats, then scores Hh*T*T
+  const int C = Hh * dh, n = blockIdx.x;
+  float* sq = sm;
+  float* sk = sq + T * C;
+  float* sv = sk + T * C;
+  float* sp = sv + T * C;
+  for (int i = threadIdx.x; i < T * 3 * C; i += blockDim.x) {
+    const int t = i / (3 * C), j = i % (3 * C);
+    const float v = __half2float(qkv[((size_t)n * T + t) * 3 * C + j]);
+    (j < C ? sq : j < 2 * C ? sk : sv)[t * C + (j % C)] = v;
+  }
+  __syncthreads();
+  const int ns = Hh * T * T;
+  if ((int)threadIdx.x < ns) {
+    const int h = threadIdx.x / (T * T), i = (threadIdx.x / T) % T, j = threadIdx.x % T;
+    float acc = 0.f;
+    for (int d = 0; d < dh; ++d) acc = fmaf(sq[i * C + h * dh + d], sk[j * C + h * dh + d], acc);
+    sp[threadIdx.x] = acc * scale;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < Hh * T) {       // softmax over j for row (h, i)
+    float* row = sp + threadIdx.x * T;
+    float m = row[0];
+    for (int j = 1; j < T; ++j) m = fmaxf(m, row[j]);
+    float s = 0.f;
+    for (int j = 0; j < T; ++j) { row[j] = __expf(row[j] - m); s += row[j]; }
+    const float inv = 1.f / s;
+    for (int j = 0; j < T; ++j) row[j] *= inv;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < T * C; i += blockDim.x) {
+    const int t = i / C, c = i % C, h = c / dh;
+    float acc = 0.f;
+    for (int j = 0; j < T; ++j) acc = fmaf(sp[(h * T + t) * T + j], sv[j * C + c], acc);
+    out[((size_t)n * T + t) * C + c] = __float2half_rn(acc);
+  }
+}
+
+// diffusers Upsample1d("cubic"): reflect pad 2, depthwise conv_transpose1d(stride 2, padding 7).  x (N,L,C) -> (N,2L,C)
+__global__ void cubic_up1d_kernel(const float* __restrict__ x, float* __restrict__ y, int L, int C, const float* __restrict__ kern,
+                                  size_t total) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int o = (int)((i / C) % (2 * L));
+    const size_t n = i / ((size_t)C * 2 * L);
+    float acc = 0.f;
+    // y[o] = sum_i xp[i] * k[o + 7 - 2 i],  xp = reflect-padded x (length L + 4)
+    for (int ii = 0; ii < L + 4; ++ii) {
+      const int kk = o + 7 - 2 * ii;
+      if (kk < 0 || kk >= 8) continue;
+      int src = ii - 2;
+      if (src < 0) src = -src;
+      if (src >= L) src = 2 * (L - 1) - src;
+      acc = fmaf(x[(n * L + src) * C + c], kern[kk], acc);
+    }
+    y[i] = acc;
+  }
+}
+
+// conv_out result (N*P, ld) fp32 -> out (N, 3, P) fp32 (first three channels)
+__global__ void slice_out_kernel(const float* __restrict__ h, int ld, float* __restrict__ out, int N, int P) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * 3 * P) return;
+  const int p = i % P, co = (i / P) % 3, n = i / (3 * P);
+  out[i] = h[((size_t)n * P + p) * ld + co];
+}
+
+inline unsigned grid_for(size_t work, int bs = 256) {
+  size_t blocks = (work + bs - 1) / bs;
+  const size_t cap = (size_t)num_sms() * 32;
+  return (unsigned)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
+
+struct Conv {      // packed convolution / linear:  out[rows, cout_pad] = A[rows, kpad] * w^T + bias
+  __half* w = nullptr;
+  float* bias = nullptr;
+  int cin = 0, cout = 0, taps = 1, kpad = 0, cout_pad = 0;
+};
+struct Norm {
+  float *g = nullptr, *b = nullptr;
+};
+struct Res2d {
+  Norm n1, n2;
+  Conv c1, c2, sc;
+  bool has_sc = false;
+};
+struct Res1d {
+  Conv c1, c2, skip;
+  Norm n1, n2;
+  bool has_skip = false;
+};
+struct Attn {
+  Norm gn;
+  Conv qkv, proj;
+};
+
+}  // namespace
+}  // namespace bg
+
+using namespace bg;
+
+struct BgVae {
+  int kind = 0;                 // 0 surface (2-D), 1 edge (1-D)
+  char* arena = nullptr;
+  size_t arena_bytes = 0;
+  float *pq_w = nullptr, *pq_b = nullptr, *up_kernel = nullptr;
+  Conv conv_in, conv_out;
+  Norm norm_out;
+  // surface
+  Res2d s_mid[2];
+  Attn s_attn;
+  Res2d s_up[4][3];
+  Conv s_upconv[3];
+  // edge
+  Res1d e_mid[6];
+  Attn e_attn[6];
+  Res1d e_up[3][3];
+};
+
+namespace {
+
+struct VPacker {
+  std::map<std::string, const BgNamedTensor*> by_name;
+  char* base = nullptr;
+  size_t off = 0;
+  bool dry = true;
+  cudaStream_t st = nullptr;
+  int err = 0;
+
+  const float* find(const std::string& name, int64_t numel) {
+    auto it = by_name.find(name);
+    if (it == by_name.end()) {
+      if (!err) err = set_error(BG_ERR_MISSING_WEIGHT, "missing weight: " + name);
+      return nullptr;
+    }
+    if (it->second->numel != numel) {
+      if (!err) err = set_error(BG_ERR_BAD_ARG, "weight " + name + " has the wrong number of elements");
+      return nullptr;
+    }
+    return it->second->data;
+  }
+  template <class T>
+  T* take(size_t n) {
+    T* p = dry ? nullptr : reinterpret_cast<T*>(base + off);
+    off += align_up(n * sizeof(T));
+    return p;
+  }
+  float* copy(const std::string& name, int64_t numel) {
+    const float* src = find(name, numel);
+    float* dst = take<float>(numel);
+    if (!dry && src && !err) err = check_cuda(cudaMemcpyAsync(dst, src, numel * 4, cudaMemcpyDeviceToDevice, st), "copy");
+    return dst;
+  }
+  float* zeros(int64_t numel) {
+    float* dst = take<float>(numel);
+    if (!dry && !err) err = check_cuda(cudaMemsetAsync(dst, 0, numel * 4, st), "memset");
+    return dst;
+  }
+  Norm norm(const std::string& name, int c) {
+    Norm n;
+    n.g = copy(name + ".weight", c);
+    n.b = copy(name + ".bias", c);
+    return n;
+  }
+  Conv conv(const std::string& name, int cout, int cin, int taps, bool bias = true, int cout_pad = 0) {
+    Conv c;
+    c.cin = cin; c.cout = cout; c.taps = taps;
+    c.kpad = round64(cin * taps);
+    c.cout_pad = cout_pad ? cout_pad : cout;
+    const float* w = find(name + ".weight", (int64_t)cout * cin * taps);
+    c.w = take<__half>((size_t)c.cout_pad * c.kpad);
+    if (!dry && w && !err) {
+      const size_t tot = (size_t)c.cout_pad * c.kpad;
+      pack_conv_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(w, c.w, cout, cin, taps, c.kpad, c.cout_pad);
+      err = check_launch("pack_conv_kernel launch");
+    }
+    if (bias) {
+      if (c.cout_pad == cout) {
+        c.bias = copy(name + ".bias", cout);
+      } else {
+        const float* b = find(name + ".bias", cout);
+        c.bias = zeros(c.cout_pad);
+        if (!dry && b && !err) err = check_cuda(cudaMemcpyAsync(c.bias, b, cout * 4, cudaMemcpyDeviceToDevice, st), "copy");
+      }
+    }
+    return c;
+  }
+  // q | k | v linears (C -> C each) concatenated into one [3C][C] operand
+  Conv qkv(const std::string& a, const char* qn, const char* kn, const char* vn, int C) {
+    Conv c;
+    c.cin = C; c.cout = 3 * C; c.taps = 1; c.kpad = C; c.cout_pad = 3 * C;
+    c.w = take<__half>((size_t)3 * C * C);
+    c.bias = take<float>(3 * C);
+    const char* names[3] = {qn, kn, vn};
+    for (int i = 0; i < 3; ++i) {
+      const float* w = find(a + "." + names[i] + ".weight", (int64_t)C * C);
+      const float* b = find(a + "." + names[i] + ".bias", C);
+      if (!dry && w && b && !err) {
+        err = launch_cast_f32_to_f16(st, w, c.w + (size_t)i * C * C, (size_t)C * C);
+        if (!err) err = check_cuda(cudaMemcpyAsync(c.bias + i * C, b, C * 4, cudaMemcpyDeviceToDevice, st), "copy");
+      }
+    }
+    return c;
+  }
+};
+
+int pack_vae(BgVae* m, VPacker& pk) {
+  const std::string d = "decoder.";
+  const int taps_in = m->kind == 0 ? 9 : 3;
+  m->pq_w = pk.copy("post_quant_conv.weight", 9);
+  m->pq_b = pk.copy("post_quant_conv.bias", 3);
+  m->conv_in = pk.conv(d + "conv_in", 512, 3, taps_in);
+  if (m->kind == 0) {
+    auto res2d = [&](const std::string& n, int cin, int cout) {
+      Res2d r;
+      r.n1 = pk.norm(n + ".norm1", cin);
+      r.c1 = pk.conv(n + ".conv1", cout, cin, 9);
+      r.n2 = pk.norm(n + ".norm2", cout);
+      r.c2 = pk.conv(n + ".conv2", cout, cout, 9);
+      r.has_sc = cin != cout;
+      if (r.has_sc) r.sc = pk.conv(n + ".conv_shortcut", cout, cin, 1);
+      return r;
+    };
+    m->s_mid[0] = res2d(d + "mid_block.resnets.0", 512, 512);
+    const std::string a = d + "mid_block.attentions.0";
+    m->s_attn.gn = pk.norm(a + ".group_norm", 512);
+    m->s_attn.qkv = pk.qkv(a, "to_q", "to_k", "to_v", 512);
+    m->s_attn.proj = pk.conv(a + ".to_out.0", 512, 512, 1);
+    m->s_mid[1] = res2d(d + "mid_block.resnets.1", 512, 512);
+    const int chans[4][2] = {{512, 512}, {512, 512}, {512, 256}, {256, 128}};
+    for (int i = 0; i < 4; ++i) {
+      for (int j = 0; j < 3; ++j)
+        m->s_up[i][j] = res2d(d + "up_blocks." + std::to_string(i) + ".resnets." + std::to_string(j),
+                              j == 0 ? chans[i][0] : chans[i][1], chans[i][1]);
+      if (i < 3) m->s_upconv[i] = pk.conv(d + "up_blocks." + std::to_string(i) + ".upsamplers.0.conv", chans[i][1], chans[i][1], 9);
+    }
+    m->norm_out = pk.norm(d + "conv_norm_out", 128);
+    m->conv_out = pk.conv(d + "conv_out", 3, 128, 9, true, 128);
+  } else {
+    auto res1d = [&](const std::string& n, int cin, int cmid, int cout) {
+      Res1d r;
+      r.has_skip = cin != cout;
+      if (r.has_skip) r.skip = pk.conv(n + ".conv_skip", cout, cin, 1, false);
+      r.c1 = pk.conv(n + ".conv_1", cmid, cin, 5);
+      r.n1 = pk.norm(n + ".group_norm_1", cmid);
+      r.c2 = pk.conv(n + ".conv_2", cout, cmid, 5);
+      r.n2 = pk.norm(n + ".group_norm_2", cout);
+      return r;
+    };
+    for (int i = 0; i < 6; ++i) m->e_mid[i] = res1d(d + "mid_block.resnets." + std::to_string(i), 512, 512, 512);
+    for (int i = 0; i < 6; ++i) {
+      const std::string a = d + "mid_block.attentions." + std::to_string(i);
+      m->e_attn[i].gn = pk.norm(a + ".group_norm", 512);
+      m->e_attn[i].qkv = pk.qkv(a, "query", "key", "value", 512);
+      m->e_attn[i].proj = pk.conv(a + ".proj_attn", 512, 512, 1);
+    }
+    const int chans[3][2] = {{512, 512}, {512, 256}, {256, 128}};
+    for (int i = 0; i < 3; ++i) {
+      const std::string b = d + "up_blocks." + std::to_string(i);
+      m->e_up[i][0] = res1d(b + ".resnets.0", chans[i][0], chans[i][0], chans[i][0]);
+      m->e_up[i][1] = res1d(b + ".resnets.1", chans[i][0], chans[i][0], chans[i][0]);
+      m->e_up[i][2] = res1d(b + ".resnets.2", chans[i][0], chans[i][0], chans[i][1]);
+    }
+    m->up_kernel = pk.copy(d + "up_blocks.0.up.kernel", 8);   // the same fixed 8-tap buffer in all three blocks
+    m->norm_out = pk.norm(d + "conv_norm_out", 128);
+    m->conv_out = pk.conv(d + "conv_out", 3, 128, 3, true, 128);
+  }
+  return pk.err;
+}
+
+// per-sample buffer sizes (elements)
+struct VaeWs {
+  float *X, *H, *S;        // fp32 activations
+  __half *T, *A, *Q;       // fp16: normalised / cast activations, im2col matrix, qkv + attention output
+  size_t bytes;
+};
+VaeWs carve_vae(char* base, int kind, size_t N) {
+  // maxima over the layer list (positions x channels per sample)
+  const size_t act = kind == 0 ? 32 * 32 * 256 : 32 * 256;                 // largest activation (elements)
+  const size_t col = kind == 0 ? (size_t)32 * 32 * 9 * 256 : (size_t)16 * 5 * 512;   // largest im2col row block
+  const size_t qkv = kind == 0 ? 16 * 2048 : 4 * 2048;                     // qkv (3C) + attention out (C)
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    char* p = base ? base + off : nullptr;
+    off += align_up(bytes, 1024);
+    return p;
+  };
+  VaeWs w;
+  w.X = reinterpret_cast<float*>(take(N * act * 4));
+  w.H = reinterpret_cast<float*>(take(N * act * 4));
+  w.S = reinterpret_cast<float*>(take(N * act * 4));
+  w.T = reinterpret_cast<__half*>(take(N * act * 2));
+  w.A = reinterpret_cast<__half*>(take(N * col * 2));
+  w.Q = reinterpret_cast<__half*>(take(N * qkv * 2));
+  w.bytes = off;
+  return w;
+}
+
+struct Ctx {
+  cudaStream_t st;
+  size_t N;
+  VaeWs w;
+};
+
+int gemm(const Ctx& c, const __half* A, int lda, const Conv& cv, size_t rows, float* out32, __half* out16, const float* resid) {
+  GemmEpilogue ep;
+  ep.out = out16 ? (void*)out16 : (void*)out32;
+  ep.out_f16 = out16 ? 1 : 0;
+  ep.ldo = cv.cout_pad;
+  ep.bias = cv.bias;
+  ep.resid = resid;
+  ep.ldr = cv.cout_pad;
+  return launch_gemm_f16(c.st, A, lda, cv.w, cv.kpad, (int)rows, cv.cout_pad, cv.kpad, ep);
+}
+int groupnorm(const Ctx& c, const float* x, int P, int C, int G, float eps, const Norm& n, int act, const float* resid,
+              float* out32, __half* out16) {
+  groupnorm_kernel<<<(unsigned)c.N, C, 0, c.st>>>(x, C, P, C, G, eps, n.g, n.b, act, resid, out32, out16);
+  return check_launch("groupnorm_kernel launch");
+}
+int im2col2d(const Ctx& c, const __half* in, int H, int W, int C, int up, int kpad) {
+  const int vec = (C % 8 == 0) ? 8 : 1;
+  const size_t tot = c.N * (size_t)(H * up) * (W * up) * (kpad / vec);
+  im2col2d_kernel<<<grid_for(tot), 256, 0, c.st>>>(in, c.w.A, H, W, C, up, kpad, tot, vec);
+  return check_launch("im2col2d_kernel launch");
+}
+int im2col1d(const Ctx& c, const __half* in, int L, int C, int ks, int kpad) {
+  const int vec = (C % 8 == 0) ? 8 : 1;
+  const size_t tot = c.N * (size_t)L * (kpad / vec);
+  im2col1d_kernel<<<grid_for(tot), 256, 0, c.st>>>(in, c.w.A, L, C, ks, kpad, tot, vec);
+  return check_launch("im2col1d_kernel launch");
+}
+int attention(const Ctx& c, int T, int Hh, int dh, float scale) {
+  const int C = Hh * dh;
+  const size_t smem = (size_t)(3 * T * C + Hh * T * T) * 4;
+  static bool configured = false;
+  if (!configured) {
+    BG_CUDA(cudaFuncSetAttribute(small_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    configured = true;
+  }
+  small_attention_kernel<<<(unsigned)c.N, 256, smem, c.st>>>(c.w.Q, c.w.Q + c.N * (size_t)T * 3 * C, T, Hh, dh, scale);
+  return check_launch("small_attention_kernel launch");
+}
+
+// x (in place, fp32 [N, P, Cout] in *px): diffusers ResnetBlock2D without time embedding
+int resnet2d(const Ctx& c, const Res2d& r, float** px, float** pfree, int HW, int H) {
+  const int cin = r.c1.cin, cout = r.c1.cout;
+  float* x = *px;
+  BG_TRY(groupnorm(c, x, HW, cin, 32, 1e-6f, r.n1, 1, nullptr, nullptr, c.w.T));
+  BG_TRY(im2col2d(c, c.w.T, H, H, cin, 1, r.c1.kpad));
+  BG_TRY(gemm(c, c.w.A, r.c1.kpad, r.c1, c.N * HW, c.w.H, nullptr, nullptr));
+  BG_TRY(groupnorm(c, c.w.H, HW, cout, 32, 1e-6f, r.n2, 1, nullptr, nullptr, c.w.T));
+  BG_TRY(im2col2d(c, c.w.T, H, H, cout, 1, r.c2.kpad));
+  if (!r.has_sc) return gemm(c, c.w.A, r.c2.kpad, r.c2, c.N * HW, x, nullptr, x);
+  // 1x1 shortcut on the raw input, then conv2 accumulates onto it
+  float* s = *pfree;
+  __half* x16 = c.w.Q;     // free here (attention scratch), large enough: N*HW*cin halves <= N*act
+  (void)x16;
+  BG_TRY(launch_cast_f32_to_f16(c.st, x, c.w.T, c.N * (size_t)HW * cin));
+  // the cast reuses T, so redo nothing: A already holds the im2col of the normalised activation
+  BG_TRY(gemm(c, c.w.T, cin, r.sc, c.N * HW, s, nullptr, nullptr));
+  BG_TRY(gemm(c, c.w.A, r.c2.kpad, r.c2, c.N * HW, s, nullptr, s));
+  *px = s;
+  *pfree = x;
+  return BG_OK;
+}
+
+int resconv1d(const Ctx& c, const Res1d& r, float** px, float** pfree, int L) {
+  const int cin = r.c1.cin, cmid = r.c1.cout, cout = r.c2.cout;
+  float* x = *px;
+  BG_TRY(launch_cast_f32_to_f16(c.st, x, c.w.T, c.N * (size_t)L * cin));
+  const float* res = x;
+  float* out = x;
+  if (r.has_skip) {
+    BG_TRY(gemm(c, c.w.T, cin, r.skip, c.N * L, *pfree, nullptr, nullptr));
+    res = *pfree;
+    out = *pfree;
+  }
+  BG_TRY(im2col1d(c, c.w.T, L, cin, 5, r.c1.kpad));
+  BG_TRY(gemm(c, c.w.A, r.c1.kpad, r.c1, c.N * L, c.w.H, nullptr, nullptr));
+  BG_TRY(groupnorm(c, c.w.H, L, cmid, 1, 1e-5f, r.n1, 2, nullptr, nullptr, c.w.T));
+  BG_TRY(im2col1d(c, c.w.T, L, cmid, 5, r.c2.kpad));
+  BG_TRY(gemm(c, c.w.A, r.c2.kpad, r.c2, c.N * L, c.w.H, nullptr, nullptr));
+  BG_TRY(groupnorm(c, c.w.H, L, cout, 1, 1e-5f, r.n2, 2, res, out, nullptr));
+  if (r.has_skip) {
+    *px = out;
+    *pfree = x;
+  }
+  return BG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bg_vae_create(int kind, const BgNamedTensor* weights, int n_weights, void* stream, BgVae** out) {
+  BG_REQUIRE((kind == 0 || kind == 1) && weights && n_weights > 0 && out, "vae_create: bad arguments");
+  BG_TRY(bg_check_device());
+  BgVae* m = new BgVae();
+  m->kind = kind;
+  VPacker pk;
+  for (int i = 0; i < n_weights; ++i) pk.by_name[weights[i].name] = &weights[i];
+  pk.st = reinterpret_cast<cudaStream_t>(stream);
+  int s = pack_vae(m, pk);
+  if (s == 0) {
+    m->arena_bytes = pk.off;
+    s = check_cuda(cudaMalloc(reinterpret_cast<void**>(&m->arena), m->arena_bytes), "cudaMalloc(vae weights)");
+  }
+  if (s == 0) {
+    pk.dry = false; pk.base = m->arena; pk.off = 0;
+    s = pack_vae(m, pk);
+  }
+  if (s != 0) {
+    bg_vae_destroy(m);
+    return s;
+  }
+  *out = m;
+  return BG_OK;
+}
+
+void bg_vae_destroy(BgVae* m) {
+  if (!m) return;
+  if (m->arena) cudaFree(m->arena);
+  delete m;
+}
+
+size_t bg_vae_workspace_bytes(const BgVae* m, int N) {
+  if (!m || N <= 0) return 0;
+  return carve_vae(nullptr, m->kind, (size_t)N).bytes + 1024;
+}
+
+int bg_vae_decode(BgVae* m, const float* z, int N, float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  BG_REQUIRE(m && z && out && workspace && N > 0, "vae_decode: bad arguments");
+  Ctx c;
+  c.st = reinterpret_cast<cudaStream_t>(stream);
+  c.N = (size_t)N;
+  char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
+  c.w = carve_vae(base, m->kind, c.N);
+  if (c.w.bytes + (size_t)(base - reinterpret_cast<char*>(workspace)) > workspace_bytes)
+    return set_error(BG_ERR_WORKSPACE, "vae_decode: workspace too small");
+  float* x = c.w.X;
+  float* spare = c.w.S;
+
+  if (m->kind == 0) {
+    int H = 4;
+    postquant_kernel<<<(N * 16 + 255) / 256, 256, 0, c.st>>>(z, m->pq_w, m->pq_b, c.w.T, N, 16);
+    BG_TRY(check_launch("postquant_kernel launch"));
+    BG_TRY(im2col2d(c, c.w.T, 4, 4, 3, 1, m->conv_in.kpad));
+    BG_TRY(gemm(c, c.w.A, m->conv_in.kpad, m->conv_in, c.N * 16, x, nullptr, nullptr));
+    BG_TRY(resnet2d(c, m->s_mid[0], &x, &spare, 16, 4));
+    {   // single-head attention over the 16 positions (legacy diffusers attention block), residual
+      BG_TRY(groupnorm(c, x, 16, 512, 32, 1e-6f, m->s_attn.gn, 0, nullptr, nullptr, c.w.T));
+      BG_TRY(gemm(c, c.w.T, 512, m->s_attn.qkv, c.N * 16, nullptr, c.w.Q, nullptr));
+      BG_TRY(attention(c, 16, 1, 512, 0.044194173824159216f));   // 1 / sqrt(512)
+      BG_TRY(gemm(c, c.w.Q + c.N * (size_t)16 * 1536, 512, m->s_attn.proj, c.N * 16, x, nullptr, x));
+    }
+    BG_TRY(resnet2d(c, m->s_mid[1], &x, &spare, 16, 4));
+    for (int i = 0; i < 4; ++i) {
+      for (int j = 0; j < 3; ++j) BG_TRY(resnet2d(c, m->s_up[i][j], &x, &spare, H * H, H));
+      if (i < 3) {
+        const Conv& uc = m->s_upconv[i];
+        BG_TRY(launch_cast_f32_to_f16(c.st, x, c.w.T, c.N * (size_t)H * H * uc.cin));
+        BG_TRY(im2col2d(c, c.w.T, H, H, uc.cin, 2, uc.kpad));
+        H *= 2;
+        BG_TRY(gemm(c, c.w.A, uc.kpad, uc, c.N * H * H, spare, nullptr, nullptr));
+        float* t = x; x = spare; spare = t;
+      }
+    }
+    BG_TRY(groupnorm(c, x, 1024, 128, 32, 1e-6f, m->norm_out, 1, nullptr, nullptr, c.w.T));
+    BG_TRY(im2col2d(c, c.w.T, 32, 32, 128, 1, m->conv_out.kpad));
+    BG_TRY(gemm(c, c.w.A, m->conv_out.kpad, m->conv_out, c.N * 1024, c.w.H, nullptr, nullptr));
+    slice_out_kernel<<<(N * 3 * 1024 + 255) / 256, 256, 0, c.st>>>(c.w.H, 128, out, N, 1024);
+    return check_launch("slice_out_kernel launch");
+  }
+
+  int L = 4;
+  postquant_kernel<<<(N * 4 + 255) / 256, 256, 0, c.st>>>(z, m->pq_w, m->pq_b, c.w.T, N, 4);
+  BG_TRY(check_launch("postquant_kernel launch"));
+  BG_TRY(im2col1d(c, c.w.T, 4, 3, 3, m->conv_in.kpad));
+  BG_TRY(gemm(c, c.w.A, m->conv_in.kpad, m->conv_in, c.N * 4, x, nullptr, nullptr));
+  for (int i = 0; i < 6; ++i) {
+    BG_TRY(resconv1d(c, m->e_mid[i], &x, &spare, 4));
+    const Attn& a = m->e_attn[i];
+    BG_TRY(groupnorm(c, x, 4, 512, 1, 1e-5f, a.gn, 0, nullptr, nullptr, c.w.T));
+    BG_TRY(gemm(c, c.w.T, 512, a.qkv, c.N * 4, nullptr, c.w.Q, nullptr));
+    BG_TRY(attention(c, 4, 16, 32, 0.17677669529663687f));      // (1/sqrt(sqrt(32)))^2
+    BG_TRY(gemm(c, c.w.Q + c.N * (size_t)4 * 1536, 512, a.proj, c.N * 4, x, nullptr, x));
+  }
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) BG_TRY(resconv1d(c, m->e_up[i][j], &x, &spare, L));
+    const int C = m->e_up[i][2].c2.cout;
+    const size_t tot = c.N * (size_t)2 * L * C;
+    cubic_up1d_kernel<<<grid_for(tot), 256, 0, c.st>>>(x, spare, L, C, m->up_kernel, tot);
+    BG_TRY(check_launch("cubic_up1d_kernel launch"));
+    float* t = x; x = spare; spare = t;
+    L *= 2;
+  }
+  BG_TRY(groupnorm(c, x, 32, 128, 32, 1e-6f, m->norm_out, 1, nullptr, nullptr, c.w.T));
+  BG_TRY(im2col1d(c, c.w.T, 32, 128, 3, m->conv_out.kpad));
+  BG_TRY(gemm(c, c.w.A, m->conv_out.kpad, m->conv_out, c.N * 32, c.w.H, nullptr, nullptr));
+  slice_out_kernel<<<(N * 3 * 32 + 255) / 256, 256, 0, c.st>>>(c.w.H, 128, out, N, 32);
+  return check_launch("slice_out_kernel launch");
+}
+
+}  // extern "C"

@@ -65,3 +65,85 @@ def denoiser_spec(kind: str, use_cf: bool) -> Spec:
     if use_cf:
         out += [("class_embed.embed.weight", (NCLASS, D))]
     return out
+
+
+# ------------------------------------------------------------------------------------------------ VAE decoders
+# Checkpoints hold the full auto-encoders; sample.py:83,98 load them with strict=False into decoder-only modules, so
+# only `decoder.*` and `post_quant_conv.*` keys matter (SURVEY.md Appendix A.1 / A.2 key lists).
+def _conv(name: str, cout: int, cin: int, *k: int, bias: bool = True) -> Spec:
+    out: Spec = [(f"{name}.weight", (cout, cin) + tuple(k))]
+    if bias:
+        out.append((f"{name}.bias", (cout,)))
+    return out
+
+
+def _norm(name: str, c: int) -> Spec:
+    return [(f"{name}.weight", (c,)), (f"{name}.bias", (c,))]
+
+
+def _resnet2d(name: str, cin: int, cout: int) -> Spec:
+    out = _norm(f"{name}.norm1", cin) + _conv(f"{name}.conv1", cout, cin, 3, 3)
+    out += _norm(f"{name}.norm2", cout) + _conv(f"{name}.conv2", cout, cout, 3, 3)
+    if cin != cout:
+        out += _conv(f"{name}.conv_shortcut", cout, cin, 1, 1)
+    return out
+
+
+def surf_decoder_spec() -> Spec:
+    """AutoencoderKLFastDecode (network.py:948-1040) = diffusers 0.27 `Decoder`, cfg sample.py:72-82:
+    block_out_channels [128,256,512,512], layers_per_block 2 (-> 3 resnets per up block), latent 3, groups 32."""
+    d = "decoder"
+    out = _conv("post_quant_conv", 3, 3, 1, 1)
+    out += _conv(f"{d}.conv_in", 512, 3, 3, 3)
+    out += _resnet2d(f"{d}.mid_block.resnets.0", 512, 512)
+    a = f"{d}.mid_block.attentions.0"
+    out += _norm(f"{a}.group_norm", 512)
+    for n in ("to_q", "to_k", "to_v"):
+        out += [(f"{a}.{n}.weight", (512, 512)), (f"{a}.{n}.bias", (512,))]
+    out += [(f"{a}.to_out.0.weight", (512, 512)), (f"{a}.to_out.0.bias", (512,))]
+    out += _resnet2d(f"{d}.mid_block.resnets.1", 512, 512)
+    chans = [(512, 512), (512, 512), (512, 256), (256, 128)]
+    for i, (cin, cout) in enumerate(chans):
+        for j in range(3):
+            out += _resnet2d(f"{d}.up_blocks.{i}.resnets.{j}", cin if j == 0 else cout, cout)
+        if i < 3:
+            out += _conv(f"{d}.up_blocks.{i}.upsamplers.0.conv", cout, cout, 3, 3)
+    out += _norm(f"{d}.conv_norm_out", 128) + _conv(f"{d}.conv_out", 3, 128, 3, 3)
+    return out
+
+
+def _resconv1d(name: str, cin: int, cmid: int, cout: int) -> Spec:
+    out: Spec = []
+    if cin != cout:
+        out += _conv(f"{name}.conv_skip", cout, cin, 1, bias=False)
+    out += _conv(f"{name}.conv_1", cmid, cin, 5) + _norm(f"{name}.group_norm_1", cmid)
+    out += _conv(f"{name}.conv_2", cout, cmid, 5) + _norm(f"{name}.group_norm_2", cout)
+    return out
+
+
+def edge_decoder_spec() -> Spec:
+    """AutoencoderKL1DFastDecode (network.py:786-858) -> Decoder1D (:188-299), cfg sample.py:86-97:
+    block_out_channels [128,256,512]; mid = 6 x (ResConvBlock + SelfAttention1d(512, 16 heads)) (network.py:51-83);
+    3 UpBlock1D (network.py:30-48) each 3 ResConvBlocks + cubic Upsample1d (buffer `up.kernel`, 8 taps)."""
+    d = "decoder"
+    out = _conv("post_quant_conv", 3, 3, 1)
+    out += _conv(f"{d}.conv_in", 512, 3, 3)
+    for i in range(6):
+        out += _resconv1d(f"{d}.mid_block.resnets.{i}", 512, 512, 512)
+    for i in range(6):
+        a = f"{d}.mid_block.attentions.{i}"
+        out += _norm(f"{a}.group_norm", 512)
+        for n in ("query", "key", "value", "proj_attn"):
+            out += [(f"{a}.{n}.weight", (512, 512)), (f"{a}.{n}.bias", (512,))]
+    for i, (cin, cout) in enumerate([(512, 512), (512, 256), (256, 128)]):
+        b = f"{d}.up_blocks.{i}"
+        out += _resconv1d(f"{b}.resnets.0", cin, cin, cin)
+        out += _resconv1d(f"{b}.resnets.1", cin, cin, cin)
+        out += _resconv1d(f"{b}.resnets.2", cin, cin, cout)
+        out += [(f"{b}.up.kernel", (8,))]
+    out += _norm(f"{d}.conv_norm_out", 128) + _conv(f"{d}.conv_out", 3, 128, 3)
+    return out
+
+
+CUBIC_UP_KERNEL = [2 * v for v in (-0.01171875, -0.03515625, 0.11328125, 0.43359375, 0.43359375, 0.11328125,
+                                   -0.03515625, -0.01171875)]   # diffusers Upsample1d("cubic") buffer (kernel * 2)

@@ -28,8 +28,9 @@ def _gen(key: str, seed: int) -> torch.Generator:
 def synth_tensor(key: str, shape: Tuple[int, ...], seed: int = 0) -> torch.Tensor:
     g = _gen(key, seed)
     shape = tuple(shape)
-    if key.endswith("up.kernel") or key.endswith("down.kernel"):
-        raise KeyError("resampling kernels are fixed buffers, not synthesised")
+    if key.endswith("up.kernel"):   # fixed resampling buffer of diffusers Upsample1d("cubic"), not a learnt weight
+        from .spec import CUBIC_UP_KERNEL
+        return torch.tensor(CUBIC_UP_KERNEL, dtype=torch.float32)
     if len(shape) >= 2:
         fan_in = 1
         for s in shape[1:]:

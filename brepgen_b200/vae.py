@@ -1,0 +1,127 @@
+"""Drop-in VAE decoders with the reference's constructor kwargs, forward signature and state-dict keys.
+
+    AutoencoderKLFastDecode(**cfg).forward(z)      network.py:948-1040   z (N,3,4,4) -> (N,3,32,32)   cfg sample.py:72-82
+    AutoencoderKL1DFastDecode(**cfg).forward(z)    network.py:786-858    z (N,3,4)   -> (N,3,32)      cfg sample.py:86-97
+
+`load_state_dict(torch.load(path), strict=False)` (sample.py:83,98) works on full auto-encoder checkpoints: only
+`decoder.*` and `post_quant_conv.*` keys exist here, everything else is reported as unexpected and ignored, exactly as with
+the reference's decoder-only modules.  Arithmetic: libbrepgen_b200.so (csrc/vae.cu).  Only the architecture the reference
+instantiates is supported (block_out_channels [128,256,512,512] / [128,256,512], layers_per_block 2, latent 3, groups 32).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _ffi
+from .models import _register_tree
+from .spec import CUBIC_UP_KERNEL, edge_decoder_spec, surf_decoder_spec
+from .synth import synth_state_dict
+
+
+class _Decoder(nn.Module):
+    kind = 0
+    chunk = 1024          # samples per library call (bounds the im2col workspace)
+
+    def __init__(self, spec, expect, cfg):
+        super().__init__()
+        for k, v in expect.items():
+            if k in cfg and list(cfg[k]) != list(v):
+                raise NotImplementedError(f"{type(self).__name__}: only {k}={v} (the reference's sample.py config) is built")
+        for key, shape in spec:
+            if key.endswith("up.kernel"):
+                parts = key.split(".")
+                mod = self
+                for p in parts[:-1]:
+                    if not hasattr(mod, p):
+                        mod.add_module(p, nn.Module())
+                    mod = getattr(mod, p)
+                mod.register_buffer("kernel", torch.tensor(CUBIC_UP_KERNEL, dtype=torch.float32))
+            else:
+                _register_tree(self, key, torch.zeros(shape) if len(shape) == 1 else torch.randn(shape) * 0.02)
+        self._handle, self._sig, self._ws = None, None, None
+
+    def _release(self):
+        if self._handle is not None:
+            _ffi.lib().bg_vae_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def _ensure(self, device):
+        sd = {k: v.detach() for k, v in self.state_dict().items()}
+        sig = tuple((v.data_ptr(), v._version) for v in sd.values())
+        if self._handle is not None and sig == self._sig:
+            return
+        self._release()
+        for k, v in sd.items():
+            if v.device != device or v.dtype != torch.float32 or not v.is_contiguous():
+                raise RuntimeError(f"parameter {k} must be contiguous fp32 on {device} (call .to(device) first)")
+        names = [k.encode() for k in sd]
+        arr = (_ffi.BgNamedTensor * len(sd))()
+        for i, (k, v) in enumerate(sd.items()):
+            arr[i].name, arr[i].data, arr[i].numel = names[i], v.data_ptr(), v.numel()
+        out = C.c_void_p()
+        _ffi.check(_ffi.lib().bg_vae_create(self.kind, arr, len(sd), _ffi.current_stream(), C.byref(out)), "bg_vae_create")
+        torch.cuda.current_stream().synchronize()
+        self._handle, self._sig = out, sig
+
+    def forward(self, z: torch.Tensor) -> torch.Tensor:
+        if not z.is_cuda:
+            raise RuntimeError("brepgen_b200 has no CPU path: z must be a CUDA tensor on an sm_100 device")
+        dev = z.device
+        z = z.detach().float().contiguous()
+        N = z.shape[0]
+        out = torch.empty((N, 3) + tuple(s * 8 for s in z.shape[2:]), device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            self._ensure(dev)
+            step = min(self.chunk, N)
+            need = _ffi.lib().bg_vae_workspace_bytes(self._handle, step)
+            if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
+                self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            for lo in range(0, N, step):
+                n = min(step, N - lo)
+                _ffi.check(_ffi.lib().bg_vae_decode(self._handle, z[lo:lo + n].data_ptr(), n, out[lo:lo + n].data_ptr(),
+                                                   self._ws.data_ptr(), self._ws.numel(), _ffi.current_stream()),
+                           "bg_vae_decode")
+        return out
+
+
+class AutoencoderKLFastDecode(_Decoder):
+    kind = 0
+    chunk = 1024
+
+    def __init__(self, in_channels=3, out_channels=3, down_block_types=None, up_block_types=None,
+                 block_out_channels=(128, 256, 512, 512), layers_per_block=2, act_fn="silu", latent_channels=3,
+                 norm_num_groups=32, sample_size=512, **unused):
+        cfg = dict(block_out_channels=block_out_channels)
+        if (in_channels, out_channels, layers_per_block, act_fn, latent_channels, norm_num_groups) != (3, 3, 2, "silu", 3, 32):
+            raise NotImplementedError("AutoencoderKLFastDecode: only the configuration of sample.py:72-82 is built")
+        super().__init__(surf_decoder_spec(), dict(block_out_channels=[128, 256, 512, 512]), cfg)
+
+
+class AutoencoderKL1DFastDecode(_Decoder):
+    kind = 1
+    chunk = 32768
+
+    def __init__(self, in_channels=3, out_channels=3, down_block_types=None, up_block_types=None,
+                 block_out_channels=(128, 256, 512), layers_per_block=2, act_fn="silu", latent_channels=3,
+                 norm_num_groups=32, sample_size=512, **unused):
+        cfg = dict(block_out_channels=block_out_channels)
+        if (in_channels, out_channels, layers_per_block, act_fn, latent_channels, norm_num_groups) != (3, 3, 2, "silu", 3, 32):
+            raise NotImplementedError("AutoencoderKL1DFastDecode: only the configuration of sample.py:86-97 is built")
+        super().__init__(edge_decoder_spec(), dict(block_out_channels=[128, 256, 512]), cfg)
+
+
+def build_synthetic_decoders(device, seed: int = 2):
+    """random-init decoders (there are no checkpoints offline) for the bench and the tests"""
+    s, e = AutoencoderKLFastDecode(), AutoencoderKL1DFastDecode()
+    s.load_state_dict(synth_state_dict(surf_decoder_spec(), seed), strict=False)
+    e.load_state_dict(synth_state_dict(edge_decoder_spec(), seed), strict=False)
+    return s.to(device).eval(), e.to(device).eval()

@@ -82,6 +82,17 @@ int bg_denoiser_forward(BgDenoiser* m, const BgDenoiserArgs* args, void* workspa
                         void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * VAE decoders.  Replace AutoencoderKLFastDecode.forward (network.py:1013-1040; kind 0: z (N,3,4,4) -> (N,3,32,32)) and
+ * AutoencoderKL1DFastDecode.forward (network.py:846-858; kind 1: z (N,3,4) -> (N,3,32)) for the configurations of
+ * sample.py:72-97.  `weights`: the `decoder.*` and `post_quant_conv.*` entries of the checkpoint (extra keys ignored).
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct BgVae BgVae;
+int bg_vae_create(int kind, const BgNamedTensor* weights, int n_weights, void* stream, BgVae** out);
+void bg_vae_destroy(BgVae* m);
+size_t bg_vae_workspace_bytes(const BgVae* m, int N);
+int bg_vae_decode(BgVae* m, const float* z, int N, float* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Scheduler updates.  Replace diffusers DDPMScheduler.step / PNDMScheduler.step as called at
  * sample.py:137,153,202,222,236,282 (arithmetic: SURVEY.md Appendix A.3/A.4).  Scalars are computed by the host-side
  * scheduler object from its alphas_cumprod table exactly as diffusers does.

@@ -1,0 +1,113 @@
+"""ORACLE (test infrastructure): CPU fp32 restatement of the two VAE decoders.
+
+PARITY UNPINNED.  The arithmetic lives in diffusers==0.27 (requirements.txt:5 of the reference), which is absent from
+/root/reference and from this image: `Decoder`, `UNetMidBlock2D`, `UpDecoderBlock2D`, `ResnetBlock2D`, `Attention`,
+`Upsample2D` (surface) and `ResConvBlock`, `SelfAttention1d`, `Upsample1d` (edge).  This file restates their published
+structure around the reference's own wrappers
+    AutoencoderKLFastDecode.forward      /root/reference/network.py:1013-1040   (cfg sample.py:72-82)
+    AutoencoderKL1DFastDecode.forward    network.py:846-858, Decoder1D :188-299, UNetMidBlock1D :51-83, UpBlock1D :30-48
+                                         (cfg sample.py:86-97)
+and is anchored on: input/output shapes consumed at sample.py:289-294, the state-dict key sets and the parameter counts
+49 485 583 / 39 124 751 (tests/test_oracle_vae.py), partition-of-unity of the cubic resampler.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict
+
+import torch
+import torch.nn.functional as F
+
+SD = Dict[str, torch.Tensor]
+
+
+def _gn(x, sd, name, groups, eps):
+    return F.group_norm(x, groups, sd[name + ".weight"], sd[name + ".bias"], eps)
+
+
+# ------------------------------------------------------------------------------------------------ surface (2-D)
+def _resnet2d(sd: SD, name: str, x):
+    h = F.conv2d(F.silu(_gn(x, sd, name + ".norm1", 32, 1e-6)), sd[name + ".conv1.weight"], sd[name + ".conv1.bias"], padding=1)
+    h = F.conv2d(F.silu(_gn(h, sd, name + ".norm2", 32, 1e-6)), sd[name + ".conv2.weight"], sd[name + ".conv2.bias"], padding=1)
+    if name + ".conv_shortcut.weight" in sd:
+        x = F.conv2d(x, sd[name + ".conv_shortcut.weight"], sd[name + ".conv_shortcut.bias"])
+    return x + h
+
+
+def _attn2d(sd: SD, name: str, x):
+    N, C, H, W = x.shape
+    h = _gn(x, sd, name + ".group_norm", 32, 1e-6).view(N, C, H * W).transpose(1, 2)          # (N, HW, C)
+    q = h @ sd[name + ".to_q.weight"].t() + sd[name + ".to_q.bias"]
+    k = h @ sd[name + ".to_k.weight"].t() + sd[name + ".to_k.bias"]
+    v = h @ sd[name + ".to_v.weight"].t() + sd[name + ".to_v.bias"]
+    a = torch.softmax(q @ k.transpose(1, 2) / math.sqrt(C), dim=-1) @ v                       # 1 head, dim_head = C
+    a = a @ sd[name + ".to_out.0.weight"].t() + sd[name + ".to_out.0.bias"]
+    return x + a.transpose(1, 2).reshape(N, C, H, W)
+
+
+def surf_decode(sd: SD, z: torch.Tensor) -> torch.Tensor:
+    """z (N,3,4,4) -> (N,3,32,32)"""
+    d = "decoder"
+    x = F.conv2d(z, sd["post_quant_conv.weight"], sd["post_quant_conv.bias"])
+    x = F.conv2d(x, sd[f"{d}.conv_in.weight"], sd[f"{d}.conv_in.bias"], padding=1)
+    x = _resnet2d(sd, f"{d}.mid_block.resnets.0", x)
+    x = _attn2d(sd, f"{d}.mid_block.attentions.0", x)
+    x = _resnet2d(sd, f"{d}.mid_block.resnets.1", x)
+    for i in range(4):
+        for j in range(3):
+            x = _resnet2d(sd, f"{d}.up_blocks.{i}.resnets.{j}", x)
+        if i < 3:
+            x = F.interpolate(x, scale_factor=2.0, mode="nearest")
+            x = F.conv2d(x, sd[f"{d}.up_blocks.{i}.upsamplers.0.conv.weight"], sd[f"{d}.up_blocks.{i}.upsamplers.0.conv.bias"],
+                         padding=1)
+    x = F.silu(_gn(x, sd, f"{d}.conv_norm_out", 32, 1e-6))
+    return F.conv2d(x, sd[f"{d}.conv_out.weight"], sd[f"{d}.conv_out.bias"], padding=1)
+
+
+# ------------------------------------------------------------------------------------------------ edge (1-D)
+def _resconv1d(sd: SD, name: str, x):
+    res = F.conv1d(x, sd[name + ".conv_skip.weight"]) if name + ".conv_skip.weight" in sd else x
+    h = F.conv1d(x, sd[name + ".conv_1.weight"], sd[name + ".conv_1.bias"], padding=2)
+    h = F.gelu(_gn(h, sd, name + ".group_norm_1", 1, 1e-5))
+    h = F.conv1d(h, sd[name + ".conv_2.weight"], sd[name + ".conv_2.bias"], padding=2)
+    h = F.gelu(_gn(h, sd, name + ".group_norm_2", 1, 1e-5))
+    return h + res
+
+
+def _attn1d(sd: SD, name: str, x, n_head: int = 16):
+    N, C, L = x.shape
+    h = _gn(x, sd, name + ".group_norm", 1, 1e-5).transpose(1, 2)                             # (N, L, C)
+    dh = C // n_head
+    proj = lambda t, w: (t @ sd[f"{name}.{w}.weight"].t() + sd[f"{name}.{w}.bias"]).view(N, L, n_head, dh).transpose(1, 2)
+    q, k, v = proj(h, "query"), proj(h, "key"), proj(h, "value")
+    scale = 1.0 / math.sqrt(math.sqrt(dh))
+    a = torch.softmax((q * scale) @ (k * scale).transpose(-1, -2), dim=-1) @ v
+    a = a.transpose(1, 2).reshape(N, L, C)
+    a = a @ sd[name + ".proj_attn.weight"].t() + sd[name + ".proj_attn.bias"]
+    return x + a.transpose(1, 2)
+
+
+def cubic_upsample1d(x, kernel):
+    """diffusers Upsample1d('cubic'): reflect pad 2, depthwise conv_transpose1d(stride 2, padding 7): L -> 2L"""
+    C = x.shape[1]
+    x = F.pad(x, (2, 2), "reflect")
+    w = x.new_zeros(C, C, kernel.shape[0])
+    idx = torch.arange(C)
+    w[idx, idx] = kernel.to(x)
+    return F.conv_transpose1d(x, w, stride=2, padding=kernel.shape[0] * 2 // 2 - 1)
+
+
+def edge_decode(sd: SD, z: torch.Tensor) -> torch.Tensor:
+    """z (N,3,4) -> (N,3,32)"""
+    d = "decoder"
+    x = F.conv1d(z, sd["post_quant_conv.weight"], sd["post_quant_conv.bias"])
+    x = F.conv1d(x, sd[f"{d}.conv_in.weight"], sd[f"{d}.conv_in.bias"], padding=1)
+    for i in range(6):
+        x = _resconv1d(sd, f"{d}.mid_block.resnets.{i}", x)
+        x = _attn1d(sd, f"{d}.mid_block.attentions.{i}", x)
+    for i in range(3):
+        for j in range(3):
+            x = _resconv1d(sd, f"{d}.up_blocks.{i}.resnets.{j}", x)
+        x = cubic_upsample1d(x, sd[f"{d}.up_blocks.{i}.up.kernel"])
+    x = F.silu(_gn(x, sd, f"{d}.conv_norm_out", 32, 1e-6))
+    return F.conv1d(x, sd[f"{d}.conv_out.weight"], sd[f"{d}.conv_out.bias"], padding=1)

@@ -1,0 +1,30 @@
+"""Structural invariants that pin the (diffusers-less) VAE decoder oracle -- SURVEY.md Appendix A.5 items 1, 3, 6."""
+import math
+
+import torch
+
+from brepgen_b200.spec import CUBIC_UP_KERNEL, edge_decoder_spec, surf_decoder_spec
+from brepgen_b200.synth import synth_state_dict
+from oracle import vae as V
+
+
+def test_parameter_counts_and_shapes():
+    n = lambda sp: sum(math.prod(s) for k, s in sp if not k.endswith("up.kernel"))
+    assert n(surf_decoder_spec()) == 49_485_583      # SD-VAE decoder 49 490 179 - 4 608 (3 vs 4 latent ch.) + 12
+    assert n(edge_decoder_spec()) == 39_124_751
+    sds, sde = synth_state_dict(surf_decoder_spec(), 3), synth_state_dict(edge_decoder_spec(), 3)
+    with torch.no_grad():
+        ys = V.surf_decode(sds, torch.randn(2, 3, 4, 4))
+        ye = V.edge_decode(sde, torch.randn(3, 3, 4))
+    assert ys.shape == (2, 3, 32, 32) and ye.shape == (3, 3, 32)      # consumed at sample.py:289-294
+    assert torch.isfinite(ys).all() and torch.isfinite(ye).all()
+
+
+def test_cubic_upsampler_partition_of_unity_and_ramp():
+    k = torch.tensor(CUBIC_UP_KERNEL)
+    assert abs(float(k[0::2].sum()) - 1) < 1e-6 and abs(float(k[1::2].sum()) - 1) < 1e-6
+    x = torch.ones(1, 4, 8)
+    assert torch.allclose(V.cubic_upsample1d(x, k), torch.ones(1, 4, 16), atol=1e-6)
+    ramp = torch.arange(16.0).view(1, 1, 16)
+    y = V.cubic_upsample1d(ramp, k)[0, 0, 8:24]          # interior: half-sample-phase ramp
+    assert torch.allclose(y[1:] - y[:-1], torch.full((15,), 0.5), atol=1e-5)
