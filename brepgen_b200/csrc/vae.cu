@@ -24,7 +24,11 @@ inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 inline int round64(int k) { return (k + 63) / 64 * 64; }
 
 // ------------------------------------------------------------------------------------------------ kernels
-// weights [Cout][Cin][taps] fp32 -> [Cout_pad][Kpad] fp16 with k = tap * Cin + cin (zero padded)
+// Compensated fp16 products.  Every GEMM of the decoders computes  A_hi W_hi + A_lo W_hi + A_hi W_lo  (hi = fp16(v),
+// lo = fp16(v - hi); only the ~2^-22 lo*lo term is dropped) as ONE GEMM over a 3x longer K: activations are stored as
+// [hi | lo] pairs (pitch 2C), weights as [W_hi | W_hi | W_lo], and the A tile wraps around after 2K columns (a_kwrap).
+// ~30 chained convolutions otherwise accumulate 1.9e-3 of fp16 rounding; decode is 0.13 % of the cascade's FLOPs.
+// weights [Cout][Cin][taps] fp32 -> [Cout_pad][3 * Kpad] fp16 with k = tap * Cin + cin (zero padded)
 __global__ void pack_conv_kernel(const float* __restrict__ w, __half* __restrict__ dst, int Cout, int Cin, int taps, int Kpad,
                                  int Cout_pad) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -35,10 +39,37 @@ __global__ void pack_conv_kernel(const float* __restrict__ w, __half* __restrict
     const int tap = k / Cin, ci = k % Cin;
     v = w[((size_t)co * Cin + ci) * taps + tap];
   }
-  dst[i] = __float2half_rn(v);
+  const __half hi = __float2half_rn(v);
+  dst[(size_t)co * 3 * Kpad + k] = hi;
+  dst[(size_t)co * 3 * Kpad + Kpad + k] = hi;
+  dst[(size_t)co * 3 * Kpad + 2 * Kpad + k] = __float2half_rn(v - __half2float(hi));
+}
+// plain linear [N][K] fp32 -> rows [row0, row0+N) of a [*][3K] hi|hi|lo operand
+__global__ void pack_linear_split_kernel(const float* __restrict__ w, __half* __restrict__ dst, int N, int K, int row0) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)N * K) return;
+  const int n = (int)(i / K), k = (int)(i % K);
+  const float v = w[i];
+  const __half hi = __float2half_rn(v);
+  dst[(size_t)(row0 + n) * 3 * K + k] = hi;
+  dst[(size_t)(row0 + n) * 3 * K + K + k] = hi;
+  dst[(size_t)(row0 + n) * 3 * K + 2 * K + k] = __float2half_rn(v - __half2float(hi));
+}
+__device__ __forceinline__ void store_hl(__half* dst, int lo_off, float v) {
+  const __half hi = __float2half_rn(v);
+  dst[0] = hi;
+  dst[lo_off] = __float2half_rn(v - __half2float(hi));
+}
+// x fp32 [rows][C] -> [rows][2C] fp16 hi|lo
+__global__ void cast_split_kernel(const float* __restrict__ x, __half* __restrict__ y, int C, size_t total) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = i / C;
+    const int c = (int)(i % C);
+    store_hl(y + row * 2 * C + c, C, x[i]);
+  }
 }
 
-// z (N, 3, P) fp32 -> y (N, P, 3) fp16, y = W z + b  (post_quant_conv, 1x1)
+// z (N, 3, P) fp32 -> y (N, P, [3 hi | 3 lo]) fp16, y = W z + b  (post_quant_conv, 1x1)
 __global__ void postquant_kernel(const float* __restrict__ z, const float* __restrict__ w, const float* __restrict__ b,
                                  __half* __restrict__ y, int N, int P) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -47,12 +78,12 @@ __global__ void postquant_kernel(const float* __restrict__ z, const float* __res
   const float z0 = z[((size_t)n * 3 + 0) * P + p], z1 = z[((size_t)n * 3 + 1) * P + p], z2 = z[((size_t)n * 3 + 2) * P + p];
 #pragma unroll
   for (int co = 0; co < 3; ++co)
-    y[(size_t)i * 3 + co] = __float2half_rn(b[co] + w[co * 3] * z0 + w[co * 3 + 1] * z1 + w[co * 3 + 2] * z2);
+    store_hl(y + (size_t)i * 6 + co, 3, b[co] + w[co * 3] * z0 + w[co * 3 + 1] * z1 + w[co * 3 + 2] * z2);
 }
 
 // in (N, H, W, C) fp16 -> A (N*Ho*Wo, Kpad) fp16, 3x3 pad 1 on the (optionally nearest-2x upsampled) image
-__global__ void im2col2d_kernel(const __half* __restrict__ in, __half* __restrict__ A, int H, int W, int C, int up, int Kpad,
-                                size_t total_vec, int vec) {
+__global__ void im2col2d_kernel(const __half* __restrict__ in, int ldin, __half* __restrict__ A, int ldA, int H, int W, int C,
+                                int up, int Kpad, size_t total_vec, int vec) {
   const int Ho = H * up, Wo = W * up;
   const int kvec = Kpad / vec;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (size_t)gridDim.x * blockDim.x) {
@@ -60,14 +91,14 @@ __global__ void im2col2d_kernel(const __half* __restrict__ in, __half* __restric
     const int k = (int)(i % kvec) * vec;
     const int x = (int)(row % Wo), y = (int)((row / Wo) % Ho);
     const size_t n = row / ((size_t)Wo * Ho);
-    __half* dst = A + row * Kpad + k;
+    __half* dst = A + row * ldA + k;
     if (vec == 8) {
       uint4 v = make_uint4(0, 0, 0, 0);
       if (k < 9 * C) {
         const int tap = k / C, c = k % C;
         const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
         if (yy >= 0 && yy < Ho && xx >= 0 && xx < Wo)
-          v = *reinterpret_cast<const uint4*>(in + ((n * H + yy / up) * W + xx / up) * C + c);
+          v = *reinterpret_cast<const uint4*>(in + ((n * H + yy / up) * W + xx / up) * ldin + c);
       }
       *reinterpret_cast<uint4*>(dst) = v;
     } else {
@@ -75,7 +106,7 @@ __global__ void im2col2d_kernel(const __half* __restrict__ in, __half* __restric
       if (k < 9 * C) {
         const int tap = k / C, c = k % C;
         const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
-        if (yy >= 0 && yy < Ho && xx >= 0 && xx < Wo) v = in[((n * H + yy / up) * W + xx / up) * C + c];
+        if (yy >= 0 && yy < Ho && xx >= 0 && xx < Wo) v = in[((n * H + yy / up) * W + xx / up) * ldin + c];
       }
       *dst = v;
     }
@@ -83,21 +114,21 @@ __global__ void im2col2d_kernel(const __half* __restrict__ in, __half* __restric
 }
 
 // in (N, L, C) fp16 -> A (N*L, Kpad) fp16, kernel size ks (odd), pad ks/2
-__global__ void im2col1d_kernel(const __half* __restrict__ in, __half* __restrict__ A, int L, int C, int ks, int Kpad,
-                                size_t total_vec, int vec) {
+__global__ void im2col1d_kernel(const __half* __restrict__ in, int ldin, __half* __restrict__ A, int ldA, int L, int C, int ks,
+                                int Kpad, size_t total_vec, int vec) {
   const int kvec = Kpad / vec;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (size_t)gridDim.x * blockDim.x) {
     const size_t row = i / kvec;
     const int k = (int)(i % kvec) * vec;
     const int l = (int)(row % L);
     const size_t n = row / L;
-    __half* dst = A + row * Kpad + k;
+    __half* dst = A + row * ldA + k;
     if (vec == 8) {
       uint4 v = make_uint4(0, 0, 0, 0);
       if (k < ks * C) {
         const int tap = k / C, c = k % C;
         const int ll = l + tap - ks / 2;
-        if (ll >= 0 && ll < L) v = *reinterpret_cast<const uint4*>(in + (n * L + ll) * C + c);
+        if (ll >= 0 && ll < L) v = *reinterpret_cast<const uint4*>(in + (n * L + ll) * ldin + c);
       }
       *reinterpret_cast<uint4*>(dst) = v;
     } else {
@@ -105,7 +136,7 @@ __global__ void im2col1d_kernel(const __half* __restrict__ in, __half* __restric
       if (k < ks * C) {
         const int tap = k / C, c = k % C;
         const int ll = l + tap - ks / 2;
-        if (ll >= 0 && ll < L) v = in[(n * L + ll) * C + c];
+        if (ll >= 0 && ll < L) v = in[(n * L + ll) * ldin + c];
       }
       *dst = v;
     }
@@ -166,7 +197,7 @@ __global__ void groupnorm_kernel(const float* __restrict__ x, int ldx, int P, in
     const size_t o = ((size_t)n * P + p) * C + c;
     if (resid) y += resid[o];
     if (out32) out32[o] = y;
-    if (out16) out16[o] = __float2half_rn(y);
+    if (out16) store_hl(out16 + ((size_t)n * P + p) * 2 * C + c, C, y);
   }
 }
 
@@ -207,7 +238,7 @@ __global__ void __launch_bounds__(256) small_attention_kernel(const __half* __re
     const int t = i / C, c = i % C, h = c / dh;
     float acc = 0.f;
     for (int j = 0; j < T; ++j) acc = fmaf(sp[(h * T + t) * T + j], sv[j * C + c], acc);
-    out[((size_t)n * T + t) * C + c] = __float2half_rn(acc);
+    store_hl(out + ((size_t)n * T + t) * 2 * C + c, C, acc);
   }
 }
 
@@ -343,7 +374,7 @@ struct VPacker {
     c.kpad = round64(cin * taps);
     c.cout_pad = cout_pad ? cout_pad : cout;
     const float* w = find(name + ".weight", (int64_t)cout * cin * taps);
-    c.w = take<__half>((size_t)c.cout_pad * c.kpad);
+    c.w = take<__half>((size_t)c.cout_pad * 3 * c.kpad);
     if (!dry && w && !err) {
       const size_t tot = (size_t)c.cout_pad * c.kpad;
       pack_conv_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(w, c.w, cout, cin, taps, c.kpad, c.cout_pad);
@@ -364,14 +395,15 @@ struct VPacker {
   Conv qkv(const std::string& a, const char* qn, const char* kn, const char* vn, int C) {
     Conv c;
     c.cin = C; c.cout = 3 * C; c.taps = 1; c.kpad = C; c.cout_pad = 3 * C;
-    c.w = take<__half>((size_t)3 * C * C);
+    c.w = take<__half>((size_t)3 * C * 3 * C);
     c.bias = take<float>(3 * C);
     const char* names[3] = {qn, kn, vn};
     for (int i = 0; i < 3; ++i) {
       const float* w = find(a + "." + names[i] + ".weight", (int64_t)C * C);
       const float* b = find(a + "." + names[i] + ".bias", C);
       if (!dry && w && b && !err) {
-        err = launch_cast_f32_to_f16(st, w, c.w + (size_t)i * C * C, (size_t)C * C);
+        pack_linear_split_kernel<<<(C * C + 255) / 256, 256, 0, st>>>(w, c.w, C, C, i * C);
+        err = check_launch("pack_linear_split_kernel launch");
         if (!err) err = check_cuda(cudaMemcpyAsync(c.bias + i * C, b, C * 4, cudaMemcpyDeviceToDevice, st), "copy");
       }
     }
@@ -453,7 +485,7 @@ VaeWs carve_vae(char* base, int kind, size_t N) {
   // maxima over the layer list (positions x channels per sample)
   const size_t act = kind == 0 ? 32 * 32 * 256 : 32 * 256;                 // largest activation (elements)
   const size_t col = kind == 0 ? (size_t)32 * 32 * 9 * 256 : (size_t)16 * 5 * 512;   // largest im2col row block
-  const size_t qkv = kind == 0 ? 16 * 2048 : 4 * 2048;                     // qkv (3C) + attention out (C)
+  const size_t qkv = kind == 0 ? 16 * 2560 : 4 * 2560;                     // qkv (3C) + attention out (2C, hi | lo)
   size_t off = 0;
   auto take = [&](size_t bytes) {
     char* p = base ? base + off : nullptr;
@@ -464,8 +496,8 @@ VaeWs carve_vae(char* base, int kind, size_t N) {
   w.X = reinterpret_cast<float*>(take(N * act * 4));
   w.H = reinterpret_cast<float*>(take(N * act * 4));
   w.S = reinterpret_cast<float*>(take(N * act * 4));
-  w.T = reinterpret_cast<__half*>(take(N * act * 2));
-  w.A = reinterpret_cast<__half*>(take(N * col * 2));
+  w.T = reinterpret_cast<__half*>(take(N * act * 2 * 2));       // [hi | lo]
+  w.A = reinterpret_cast<__half*>(take(N * col * 2 * 2));       // [A_hi | A_lo]
   w.Q = reinterpret_cast<__half*>(take(N * qkv * 2));
   w.bytes = off;
   return w;
@@ -477,7 +509,8 @@ struct Ctx {
   VaeWs w;
 };
 
-int gemm(const Ctx& c, const __half* A, int lda, const Conv& cv, size_t rows, float* out32, __half* out16, const float* resid) {
+// A: [rows][2 * cv.kpad] fp16 = [A_hi | A_lo]
+int gemm(const Ctx& c, const __half* A, const Conv& cv, size_t rows, float* out32, __half* out16, const float* resid) {
   GemmEpilogue ep;
   ep.out = out16 ? (void*)out16 : (void*)out32;
   ep.out_f16 = out16 ? 1 : 0;
@@ -485,24 +518,36 @@ int gemm(const Ctx& c, const __half* A, int lda, const Conv& cv, size_t rows, fl
   ep.bias = cv.bias;
   ep.resid = resid;
   ep.ldr = cv.cout_pad;
-  return launch_gemm_f16(c.st, A, lda, cv.w, cv.kpad, (int)rows, cv.cout_pad, cv.kpad, ep);
+  ep.a_kwrap = 2 * cv.kpad;      // [A_hi | A_lo | A_hi] x [W_hi | W_hi | W_lo]
+  return launch_gemm_f16(c.st, A, 2 * cv.kpad, cv.w, 3 * cv.kpad, (int)rows, cv.cout_pad, 3 * cv.kpad, ep);
 }
 int groupnorm(const Ctx& c, const float* x, int P, int C, int G, float eps, const Norm& n, int act, const float* resid,
               float* out32, __half* out16) {
   groupnorm_kernel<<<(unsigned)c.N, C, 0, c.st>>>(x, C, P, C, G, eps, n.g, n.b, act, resid, out32, out16);
   return check_launch("groupnorm_kernel launch");
 }
+int cast_split(const Ctx& c, const float* x, __half* y, int C, size_t rows) {
+  const size_t tot = rows * C;
+  cast_split_kernel<<<grid_for(tot), 256, 0, c.st>>>(x, y, C, tot);
+  return check_launch("cast_split_kernel launch");
+}
 int im2col2d(const Ctx& c, const __half* in, int H, int W, int C, int up, int kpad) {
   const int vec = (C % 8 == 0) ? 8 : 1;
   const size_t tot = c.N * (size_t)(H * up) * (W * up) * (kpad / vec);
-  im2col2d_kernel<<<grid_for(tot), 256, 0, c.st>>>(in, c.w.A, H, W, C, up, kpad, tot, vec);
-  return check_launch("im2col2d_kernel launch");
+  for (int part = 0; part < 2; ++part) {   // hi plane, then lo plane of the [hi | lo] activation
+    im2col2d_kernel<<<grid_for(tot), 256, 0, c.st>>>(in + part * C, 2 * C, c.w.A + part * kpad, 2 * kpad, H, W, C, up, kpad, tot, vec);
+    BG_TRY(check_launch("im2col2d_kernel launch"));
+  }
+  return BG_OK;
 }
 int im2col1d(const Ctx& c, const __half* in, int L, int C, int ks, int kpad) {
   const int vec = (C % 8 == 0) ? 8 : 1;
   const size_t tot = c.N * (size_t)L * (kpad / vec);
-  im2col1d_kernel<<<grid_for(tot), 256, 0, c.st>>>(in, c.w.A, L, C, ks, kpad, tot, vec);
-  return check_launch("im2col1d_kernel launch");
+  for (int part = 0; part < 2; ++part) {
+    im2col1d_kernel<<<grid_for(tot), 256, 0, c.st>>>(in + part * C, 2 * C, c.w.A + part * kpad, 2 * kpad, L, C, ks, kpad, tot, vec);
+    BG_TRY(check_launch("im2col1d_kernel launch"));
+  }
+  return BG_OK;
 }
 int attention(const Ctx& c, int T, int Hh, int dh, float scale) {
   const int C = Hh * dh;
@@ -512,7 +557,7 @@ int attention(const Ctx& c, int T, int Hh, int dh, float scale) {
     BG_CUDA(cudaFuncSetAttribute(small_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     configured = true;
   }
-  small_attention_kernel<<<(unsigned)c.N, 256, smem, c.st>>>(c.w.Q, c.w.Q + c.N * (size_t)T * 3 * C, T, Hh, dh, scale);
+  small_attention_kernel<<<(unsigned)c.N, 256, smem, c.st>>>(c.w.Q, c.w.Q + c.N * (size_t)T * 3 * C, T, Hh, dh, scale);   // out: [N*T][2C]
   return check_launch("small_attention_kernel launch");
 }
 
@@ -522,18 +567,15 @@ int resnet2d(const Ctx& c, const Res2d& r, float** px, float** pfree, int HW, in
   float* x = *px;
   BG_TRY(groupnorm(c, x, HW, cin, 32, 1e-6f, r.n1, 1, nullptr, nullptr, c.w.T));
   BG_TRY(im2col2d(c, c.w.T, H, H, cin, 1, r.c1.kpad));
-  BG_TRY(gemm(c, c.w.A, r.c1.kpad, r.c1, c.N * HW, c.w.H, nullptr, nullptr));
+  BG_TRY(gemm(c, c.w.A, r.c1, c.N * HW, c.w.H, nullptr, nullptr));
   BG_TRY(groupnorm(c, c.w.H, HW, cout, 32, 1e-6f, r.n2, 1, nullptr, nullptr, c.w.T));
   BG_TRY(im2col2d(c, c.w.T, H, H, cout, 1, r.c2.kpad));
-  if (!r.has_sc) return gemm(c, c.w.A, r.c2.kpad, r.c2, c.N * HW, x, nullptr, x);
+  if (!r.has_sc) return gemm(c, c.w.A, r.c2, c.N * HW, x, nullptr, x);
   // 1x1 shortcut on the raw input, then conv2 accumulates onto it
   float* s = *pfree;
-  __half* x16 = c.w.Q;     // free here (attention scratch), large enough: N*HW*cin halves <= N*act
-  (void)x16;
-  BG_TRY(launch_cast_f32_to_f16(c.st, x, c.w.T, c.N * (size_t)HW * cin));
-  // the cast reuses T, so redo nothing: A already holds the im2col of the normalised activation
-  BG_TRY(gemm(c, c.w.T, cin, r.sc, c.N * HW, s, nullptr, nullptr));
-  BG_TRY(gemm(c, c.w.A, r.c2.kpad, r.c2, c.N * HW, s, nullptr, s));
+  BG_TRY(cast_split(c, x, c.w.T, cin, c.N * (size_t)HW));   // T is free again: A already holds conv2's im2col
+  BG_TRY(gemm(c, c.w.T, r.sc, c.N * HW, s, nullptr, nullptr));
+  BG_TRY(gemm(c, c.w.A, r.c2, c.N * HW, s, nullptr, s));
   *px = s;
   *pfree = x;
   return BG_OK;
@@ -542,19 +584,19 @@ int resnet2d(const Ctx& c, const Res2d& r, float** px, float** pfree, int HW, in
 int resconv1d(const Ctx& c, const Res1d& r, float** px, float** pfree, int L) {
   const int cin = r.c1.cin, cmid = r.c1.cout, cout = r.c2.cout;
   float* x = *px;
-  BG_TRY(launch_cast_f32_to_f16(c.st, x, c.w.T, c.N * (size_t)L * cin));
+  BG_TRY(cast_split(c, x, c.w.T, cin, c.N * (size_t)L));
   const float* res = x;
   float* out = x;
   if (r.has_skip) {
-    BG_TRY(gemm(c, c.w.T, cin, r.skip, c.N * L, *pfree, nullptr, nullptr));
+    BG_TRY(gemm(c, c.w.T, r.skip, c.N * L, *pfree, nullptr, nullptr));
     res = *pfree;
     out = *pfree;
   }
   BG_TRY(im2col1d(c, c.w.T, L, cin, 5, r.c1.kpad));
-  BG_TRY(gemm(c, c.w.A, r.c1.kpad, r.c1, c.N * L, c.w.H, nullptr, nullptr));
+  BG_TRY(gemm(c, c.w.A, r.c1, c.N * L, c.w.H, nullptr, nullptr));
   BG_TRY(groupnorm(c, c.w.H, L, cmid, 1, 1e-5f, r.n1, 2, nullptr, nullptr, c.w.T));
   BG_TRY(im2col1d(c, c.w.T, L, cmid, 5, r.c2.kpad));
-  BG_TRY(gemm(c, c.w.A, r.c2.kpad, r.c2, c.N * L, c.w.H, nullptr, nullptr));
+  BG_TRY(gemm(c, c.w.A, r.c2, c.N * L, c.w.H, nullptr, nullptr));
   BG_TRY(groupnorm(c, c.w.H, L, cout, 1, 1e-5f, r.n2, 2, res, out, nullptr));
   if (r.has_skip) {
     *px = out;
@@ -620,29 +662,29 @@ int bg_vae_decode(BgVae* m, const float* z, int N, float* out, void* workspace, 
     postquant_kernel<<<(N * 16 + 255) / 256, 256, 0, c.st>>>(z, m->pq_w, m->pq_b, c.w.T, N, 16);
     BG_TRY(check_launch("postquant_kernel launch"));
     BG_TRY(im2col2d(c, c.w.T, 4, 4, 3, 1, m->conv_in.kpad));
-    BG_TRY(gemm(c, c.w.A, m->conv_in.kpad, m->conv_in, c.N * 16, x, nullptr, nullptr));
+    BG_TRY(gemm(c, c.w.A, m->conv_in, c.N * 16, x, nullptr, nullptr));
     BG_TRY(resnet2d(c, m->s_mid[0], &x, &spare, 16, 4));
     {   // single-head attention over the 16 positions (legacy diffusers attention block), residual
       BG_TRY(groupnorm(c, x, 16, 512, 32, 1e-6f, m->s_attn.gn, 0, nullptr, nullptr, c.w.T));
-      BG_TRY(gemm(c, c.w.T, 512, m->s_attn.qkv, c.N * 16, nullptr, c.w.Q, nullptr));
+      BG_TRY(gemm(c, c.w.T, m->s_attn.qkv, c.N * 16, nullptr, c.w.Q, nullptr));
       BG_TRY(attention(c, 16, 1, 512, 0.044194173824159216f));   // 1 / sqrt(512)
-      BG_TRY(gemm(c, c.w.Q + c.N * (size_t)16 * 1536, 512, m->s_attn.proj, c.N * 16, x, nullptr, x));
+      BG_TRY(gemm(c, c.w.Q + c.N * (size_t)16 * 1536, m->s_attn.proj, c.N * 16, x, nullptr, x));
     }
     BG_TRY(resnet2d(c, m->s_mid[1], &x, &spare, 16, 4));
     for (int i = 0; i < 4; ++i) {
       for (int j = 0; j < 3; ++j) BG_TRY(resnet2d(c, m->s_up[i][j], &x, &spare, H * H, H));
       if (i < 3) {
         const Conv& uc = m->s_upconv[i];
-        BG_TRY(launch_cast_f32_to_f16(c.st, x, c.w.T, c.N * (size_t)H * H * uc.cin));
+        BG_TRY(cast_split(c, x, c.w.T, uc.cin, c.N * (size_t)H * H));
         BG_TRY(im2col2d(c, c.w.T, H, H, uc.cin, 2, uc.kpad));
         H *= 2;
-        BG_TRY(gemm(c, c.w.A, uc.kpad, uc, c.N * H * H, spare, nullptr, nullptr));
+        BG_TRY(gemm(c, c.w.A, uc, c.N * H * H, spare, nullptr, nullptr));
         float* t = x; x = spare; spare = t;
       }
     }
     BG_TRY(groupnorm(c, x, 1024, 128, 32, 1e-6f, m->norm_out, 1, nullptr, nullptr, c.w.T));
     BG_TRY(im2col2d(c, c.w.T, 32, 32, 128, 1, m->conv_out.kpad));
-    BG_TRY(gemm(c, c.w.A, m->conv_out.kpad, m->conv_out, c.N * 1024, c.w.H, nullptr, nullptr));
+    BG_TRY(gemm(c, c.w.A, m->conv_out, c.N * 1024, c.w.H, nullptr, nullptr));
     slice_out_kernel<<<(N * 3 * 1024 + 255) / 256, 256, 0, c.st>>>(c.w.H, 128, out, N, 1024);
     return check_launch("slice_out_kernel launch");
   }
@@ -651,14 +693,14 @@ int bg_vae_decode(BgVae* m, const float* z, int N, float* out, void* workspace, 
   postquant_kernel<<<(N * 4 + 255) / 256, 256, 0, c.st>>>(z, m->pq_w, m->pq_b, c.w.T, N, 4);
   BG_TRY(check_launch("postquant_kernel launch"));
   BG_TRY(im2col1d(c, c.w.T, 4, 3, 3, m->conv_in.kpad));
-  BG_TRY(gemm(c, c.w.A, m->conv_in.kpad, m->conv_in, c.N * 4, x, nullptr, nullptr));
+  BG_TRY(gemm(c, c.w.A, m->conv_in, c.N * 4, x, nullptr, nullptr));
   for (int i = 0; i < 6; ++i) {
     BG_TRY(resconv1d(c, m->e_mid[i], &x, &spare, 4));
     const Attn& a = m->e_attn[i];
     BG_TRY(groupnorm(c, x, 4, 512, 1, 1e-5f, a.gn, 0, nullptr, nullptr, c.w.T));
-    BG_TRY(gemm(c, c.w.T, 512, a.qkv, c.N * 4, nullptr, c.w.Q, nullptr));
+    BG_TRY(gemm(c, c.w.T, a.qkv, c.N * 4, nullptr, c.w.Q, nullptr));
     BG_TRY(attention(c, 4, 16, 32, 0.17677669529663687f));      // (1/sqrt(sqrt(32)))^2
-    BG_TRY(gemm(c, c.w.Q + c.N * (size_t)4 * 1536, 512, a.proj, c.N * 4, x, nullptr, x));
+    BG_TRY(gemm(c, c.w.Q + c.N * (size_t)4 * 1536, a.proj, c.N * 4, x, nullptr, x));
   }
   for (int i = 0; i < 3; ++i) {
     for (int j = 0; j < 3; ++j) BG_TRY(resconv1d(c, m->e_up[i][j], &x, &spare, L));
@@ -671,7 +713,7 @@ int bg_vae_decode(BgVae* m, const float* z, int N, float* out, void* workspace, 
   }
   BG_TRY(groupnorm(c, x, 32, 128, 32, 1e-6f, m->norm_out, 1, nullptr, nullptr, c.w.T));
   BG_TRY(im2col1d(c, c.w.T, 32, 128, 3, m->conv_out.kpad));
-  BG_TRY(gemm(c, c.w.A, m->conv_out.kpad, m->conv_out, c.N * 32, c.w.H, nullptr, nullptr));
+  BG_TRY(gemm(c, c.w.A, m->conv_out, c.N * 32, c.w.H, nullptr, nullptr));
   slice_out_kernel<<<(N * 3 * 32 + 255) / 256, 256, 0, c.st>>>(c.w.H, 128, out, N, 32);
   return check_launch("slice_out_kernel launch");
 }
