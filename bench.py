@@ -75,7 +75,7 @@ def cascade_flops_per_brep(S0, S, E, steps=1000):
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline (oracle port)
-def cpu_reference_sample(S0, S, E, reps):
+def cpu_reference_sample(S0, S, E, reps, threads=None):
     """Times the oracle (CPU fp32 restatement of the reference, pinned to its own classes) on the host cores: per stage,
     one forward + scheduler step at batch 1, `reps` timed repetitions after one warm-up; extrapolated to the
     4 x 1000-step cascade.  Returns (B-reps/s, cores, description)."""
@@ -84,7 +84,7 @@ def cpu_reference_sample(S0, S, E, reps):
     from oracle import denoisers as O
     from oracle.schedulers import DDPMOracle
 
-    cores = os.cpu_count() or 1
+    cores = threads or (os.cpu_count() or 1)
     torch.set_num_threads(cores)
     orc = DDPMOracle()
     g = torch.Generator().manual_seed(0)
@@ -113,6 +113,25 @@ def cpu_reference_sample(S0, S, E, reps):
     desc = ("oracle fp32 (torch CPU), batch 1, 1 warm + %d timed (forward + DDPM step) per stage; s/step: " % reps +
             ", ".join(f"{k}={v:.3f}" for k, v in per.items()) + "; extrapolated to 750/250 + 3x1000 steps")
     return 1.0 / sec_per_brep, cores, desc
+
+
+def best_cpu_threads():
+    """torch's intra-op pool does not scale to every hardware thread of a many-core host on these small matrices: probe
+    a few thread counts on one encoder-sized matmul chain and keep the fastest (all of them are 'threads it can use')."""
+    n = os.cpu_count() or 1
+    a, w = torch.randn(4000, 768), torch.randn(2304, 768)
+    best, best_t = n, None
+    for k in sorted({n, max(1, n // 2), max(1, n // 4), min(n, 32), min(n, 16), min(n, 8)}):
+        torch.set_num_threads(k)
+        (a @ w.t()).sum()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            q = a @ w.t()
+            torch.softmax(q[:, :768] @ q[:, 768:1536].t(), -1).sum()
+        dt = time.perf_counter() - t0
+        if best_t is None or dt < best_t:
+            best, best_t = k, dt
+    return best
 
 
 # ------------------------------------------------------------------------------------------------ clocks sampler
@@ -155,11 +174,12 @@ def run_reference(args):
     S0, E = args.surfaces, args.edges
     S = 2 * S0
     vals = []
+    nthr = best_cpu_threads()
     for _ in range(max(args.warmup, 0)):
-        cpu_reference_sample(S0, S, E, 1)
+        cpu_reference_sample(S0, S, E, 1, nthr)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        v, cores, desc = cpu_reference_sample(S0, S, E, 1)
+        v, cores, desc = cpu_reference_sample(S0, S, E, 1, nthr)
         vals.append(v)
     ms = (time.perf_counter() - t0) / max(args.steps, 1) * 1e3
     v = sum(vals) / len(vals)
@@ -248,7 +268,17 @@ def main():
     launches = _ffi.lib().bg_launch_count() - l0
     clk = clocks.finish()
     scale = 1000.0 / T
-    value = world * B / (ms / 1e3 * scale)
+    # the two VAE decodes run once per cascade whatever T is: time them alone and keep them out of the 1000/T scaling
+    ms_dec = 0.0
+    if surf_vae is not None:
+        zs = torch.randn(B * S, 3, 4, 4, device=dev)
+        ze = torch.randn(B * S * E, 3, 4, device=dev)
+        dec = lambda: (surf_vae(zs), edge_vae(ze))
+        dec()
+        ms_dec = timed(dec, max(1, args.steps))
+        del zs, ze
+    norm_ms = lambda m: (m - ms_dec) * scale + ms_dec          # ms per batch at 1000 steps per stage
+    value = world * B / (norm_ms(ms) / 1e3)
 
     # end to end through the public API: pinned host noise in, every output back to pinned host memory, per step
     e2e = None
@@ -267,7 +297,7 @@ def main():
         ms_e = timed(step_e2e, args.steps)
         h2d = sum(v.numel() * v.element_size() for v in host_in.values())
         d2h = sum(v.numel() * v.element_size() for v in host_out.values())
-        e2e = {"value": world * B / (ms_e / 1e3 * scale), "unit": UNIT, "h2d_bytes_per_step": h2d,
+        e2e = {"value": world * B / (norm_ms(ms_e) / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e}
 
     # roofline of the dominant kernel (edge-stage flash attention, L = S*E), timed alone with CUDA events
@@ -292,7 +322,7 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cores, desc = cpu_reference_sample(S0, S, E, 2)
+        v, cores, desc = cpu_reference_sample(S0, S, E, 1, best_cpu_threads())
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
 
     if rank == 0:
@@ -302,7 +332,7 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": f"abc_cascade B={B}/GPU S0={S0}->S={S} E={E} L_edge={L}, dense masks",
                            "ddpm_steps_per_stage_timed": T, "value_normalised_to_steps_per_stage": 1000,
-                           "vae_decode_in_step": surf_vae is not None,
+                           "vae_decode_in_step": surf_vae is not None, "vae_decode_ms_per_step": ms_dec,
                            "l2": "activations of one step (GBs) exceed the 126 MB L2; no explicit flush",
                            "precision": models["surfpos"].precision, "parallelism": f"batch-sharded x{world}, no collective"},
                 "roofline": roofline, "whole_cascade": whole, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
