@@ -52,7 +52,7 @@ struct ACfg {
   static constexpr int TMEM_COLS = (NT == 2) ? 512 : 256;
   // NT == 2: three full warpgroups (2 softmax + 1 for the producer / MMA warps) so setmaxnreg can move registers
   static constexpr int THREADS = (NT == 2) ? 384 : NT * 128 + 64;
-  static constexpr int TILE_COLS = 192;   // per tile: S at +0 (128 cols), PV at +128 (64 cols)
+  static constexpr int TILE_COLS = 256;   // per tile: S at +0 (128 cols), O at +128 (64), P (fp16 pairs, PT mode) at +192 (64)
 };
 
 struct AttnParams {
@@ -67,7 +67,10 @@ struct AttnParams {
 
 // PM: 4-bit mask over the 4 element pairs of each 8-key chunk whose exp2 runs as a polynomial on the FMA pipe instead of
 // MUFU.EX2 (the XU pipe, 16 ex2/clk/SM, is the binding unit of d=64 attention on B200)
-template <int NT, int PM>
+// PT: P goes to TENSOR MEMORY (tcgen05.st, two fp16 per column) and the PV MMA takes its A operand from TMEM -- per key
+// block this removes 64 KB of shared-memory writes + 64 KB of reads, which otherwise make the kernel smem-bandwidth bound
+// (QK^T and PV operand reads + P + TMA fills = 256 KB per block ~ 2048 cycles at 128 B/clk vs 1024 MMA cycles).
+template <int NT, int PM, int PT>
 __global__ void __launch_bounds__(ACfg<NT>::THREADS, (NT == 2) ? 1 : 2)
 attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   using C = ACfg<NT>;
@@ -184,9 +187,13 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
           const uint32_t p_addr = smem_u32(smem + C::OFF_P + (t * C::PB + i % C::PB) * P_BYTES);
 #pragma unroll
           for (int k = 0; k < 128 / 16; ++k)
-            umma_f16_ss(tmem_base + t * C::TILE_COLS + 128,
-                        make_sw128_desc(p_addr + (k >> 2) * (P_BYTES / 2) + (k & 3) * 32),
-                        make_sw128_desc(v_addr + k * 2048), idesc_pv, (i | k) != 0 ? 1u : 0u);
+            if (PT)   // A = P from TMEM: lane = query row, 8 columns (16 fp16) per K = 16 step
+              umma_f16_ts(tmem_base + t * C::TILE_COLS + 128, tmem_base + t * C::TILE_COLS + 192 + k * 8,
+                          make_sw128_desc(v_addr + k * 2048), idesc_pv, (i | k) != 0 ? 1u : 0u);
+            else
+              umma_f16_ss(tmem_base + t * C::TILE_COLS + 128,
+                          make_sw128_desc(p_addr + (k >> 2) * (P_BYTES / 2) + (k & 3) * 32),
+                          make_sw128_desc(v_addr + k * 2048), idesc_pv, (i | k) != 0 ? 1u : 0u);
           umma_commit(&pv_full[t * C::PB + i % C::PB]);
           umma_commit(&v_empty[s]);
         }
@@ -246,15 +253,15 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
         for (int i = 0; i < 128; ++i)
           if ((inval[i >> 5] >> (i & 31)) & 1u) s[i] = -INFINITY;
       }
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+      float mx[8];
 #pragma unroll
-      for (int i = 0; i < 128; i += 8) {       // four independent FMNMX3 chains
-        mx0 = fmax3(mx0, s[i], s[i + 1]);
-        mx1 = fmax3(mx1, s[i + 2], s[i + 3]);
-        mx2 = fmax3(mx2, s[i + 4], s[i + 5]);
-        mx3 = fmax3(mx3, s[i + 6], s[i + 7]);
+      for (int j = 0; j < 8; ++j) mx[j] = fmaxf(s[2 * j], s[2 * j + 1]);
+#pragma unroll
+      for (int i = 16; i < 128; i += 16) {     // eight independent FMNMX3 chains
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mx[j] = fmax3(mx[j], s[i + 2 * j], s[i + 2 * j + 1]);
       }
-      const float m_new = fmaxf(fmax3(m_ref, mx0, mx1), fmaxf(mx2, mx3));
+      const float m_new = fmaxf(fmax3(m_ref, fmax3(mx[0], mx[1], mx[2]), fmax3(mx[3], mx[4], mx[5])), fmaxf(mx[6], mx[7]));
 
       if (it == 0) {
         m_ref = (m_new == -INFINITY) ? 0.f : m_new;
@@ -293,27 +300,62 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
       const float2 c2 = make_float2(c, c);
       const float2 nmc2 = make_float2(-m_ref * c, -m_ref * c);
 
-      // p = exp2(c s - c m_ref), row sum (packed f32x2 math), fp16 P into the K-major SW128 layout
+      // p = exp2(c s - c m_ref), row sum (packed f32x2 math), fp16 P into the K-major SW128 layout.
+      // Software-pipelined by one 16-key group: the 16 MUFU.EX2 of group g are issued back to back, and only then are
+      // the results of group g-1 summed, packed and stored -- a consumer placed right behind its MUFU would stall the
+      // (in-order) warp for the MUFU latency and leave the XU pipe idle.
       float2 acc = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+      float2 ecur[8], eprev[8];
+      uint32_t ppk[PT ? 64 : 1];        // PT: the packed fp16 row, stored to TMEM after the loop
+      auto exp_group = [&](int g, float2 (&e)[8]) {
 #pragma unroll
-      for (int j8 = 0; j8 < 16; ++j8) {                      // 16-byte chunk (8 keys) index along the 128 keys
-        uint32_t pk[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float2 a = ffma2(make_float2(s[8 * j8 + 2 * q], s[8 * j8 + 2 * q + 1]), c2, nmc2);
-          const float2 e = ((PM >> q) & 1) ? exp2_poly2(a) : make_float2(ex2(a.x), ex2(a.y));
-          if (q & 1) acc1 = fadd2(acc1, e); else acc = fadd2(acc, e);
-          __half2 h = __floats2half2_rn(e.x, e.y);
-          pk[q] = *reinterpret_cast<uint32_t*>(&h);
+        for (int q = 0; q < 8; ++q) {
+          const float2 a = ffma2(make_float2(s[16 * g + 2 * q], s[16 * g + 2 * q + 1]), c2, nmc2);
+          e[q] = ((PM >> (q & 3)) & 1) ? exp2_poly2(a) : make_float2(ex2(a.x), ex2(a.y));
         }
-        st_shared_v4(sP + (j8 >> 3) * (P_BYTES / 2) + (((j8 & 7) ^ (r & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+      };
+      auto drain_group = [&](int g, const float2 (&e)[8]) {
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 v = e[4 * hh + q];
+            if (q & 1) acc1 = fadd2(acc1, v); else acc = fadd2(acc, v);
+            __half2 h = __floats2half2_rn(v.x, v.y);
+            pk[q] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          const int j8 = 2 * g + hh;                         // 16-byte chunk (8 keys) index along the 128 keys
+          if (PT) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) ppk[4 * j8 + q] = pk[q];
+          } else {
+            st_shared_v4(sP + (j8 >> 3) * (P_BYTES / 2) + (((j8 & 7) ^ (r & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+          }
+        }
+      };
+      exp_group(0, eprev);
+#pragma unroll
+      for (int g = 1; g < 8; ++g) {
+        exp_group(g, ecur);
+        drain_group(g - 1, eprev);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) eprev[q] = ecur[q];
       }
+      drain_group(7, eprev);
 #ifdef BG_ATTN_TRACE
       tr[6] = clock64();
 #endif
       if (NT == 2 && !(t == 1 && it == nblk - 1)) named_bar_arrive(1 + (1 - t), 256);   // hand the XU token over
       tc_fence_before();                // orders the (rare) O rescale before the PV MMA that p_full releases
-      fence_proxy_async_smem();         // generic-proxy writes of P -> visible to the tensor core (async proxy)
+      if (PT) {
+        tmem_st_32x32b_x32(s_tmem + 192, ppk);
+        tmem_st_32x32b_x32(s_tmem + 192 + 32, ppk + 32);
+        tmem_st_wait();
+        tc_fence_before();
+      } else {
+        fence_proxy_async_smem();       // generic-proxy writes of P -> visible to the tensor core (async proxy)
+      }
       mbar_arrive(&p_full[t]);
 #ifdef BG_ATTN_TRACE
       tr[7] = clock64();
@@ -383,17 +425,17 @@ __global__ void block_list_kernel(const uint8_t* __restrict__ key_mask, int L, i
   }
 }
 
-template <int NT, int PM>
+template <int NT, int PM, int PT>
 int launch_nt(cudaStream_t st, const CUtensorMap& tm, const AttnParams& p) {
   using C = ACfg<NT>;
   static bool configured = false;
   if (!configured) {
-    BG_CUDA(cudaFuncSetAttribute(attn_kernel<NT, PM>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    BG_CUDA(cudaFuncSetAttribute(attn_kernel<NT, PM, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     configured = true;
   }
   const int nq = (p.L + 127) / 128;
   dim3 grid((nq + NT - 1) / NT, NHEAD, p.B);
-  attn_kernel<NT, PM><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(tm, p);
+  attn_kernel<NT, PM, PT><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(tm, p);
   return check_launch("attn_kernel launch");
 }
 
@@ -410,15 +452,31 @@ int launch_attention(cudaStream_t st, const AttnArgs& a) {
   p.out = a.out; p.ldo = a.ldo; p.B = a.B; p.L = a.L; p.nkb = (a.L + 127) / 128;
   p.key_mask = a.key_mask; p.blk_list = a.blk_list; p.blk_count = a.blk_count;
   p.scale_log2 = 1.4426950408889634f / 8.0f;
-  if (a.L <= 128) return launch_nt<1, 0>(st, tm, p);
+  if (a.L <= 128) return launch_nt<1, 0, 0>(st, tm, p);
   static int poly = -1;                 // BG_ATTN_POLY = 0 | 1 (25 % of the exponentials) | 2 (50 %); tuning knob
   if (poly < 0) {
     const char* e = getenv("BG_ATTN_POLY");
     poly = e ? atoi(e) : 1;
   }
-  if (poly == 0) return launch_nt<2, 0x0>(st, tm, p);
-  if (poly == 2) return launch_nt<2, 0xA>(st, tm, p);
-  return launch_nt<2, 0x8>(st, tm, p);
+  static int rowsplit = -1;             // BG_ATTN_RS = 1: row-split kernel (attn_rs.cu), 16 softmax warps per CTA
+  if (rowsplit < 0) {
+    const char* e = getenv("BG_ATTN_RS");
+    rowsplit = e ? atoi(e) : 0;
+  }
+  if (rowsplit) return launch_attention_rowsplit(st, a, poly);
+  static int ptmem = -1;                // BG_ATTN_PT = 1: P in tensor memory (A operand of the PV MMA from TMEM)
+  if (ptmem < 0) {
+    const char* e = getenv("BG_ATTN_PT");
+    ptmem = e ? atoi(e) : 0;
+  }
+  if (ptmem) {
+    if (poly == 0) return launch_nt<2, 0x0, 1>(st, tm, p);
+    if (poly == 2) return launch_nt<2, 0xA, 1>(st, tm, p);
+    return launch_nt<2, 0x8, 1>(st, tm, p);
+  }
+  if (poly == 0) return launch_nt<2, 0x0, 0>(st, tm, p);
+  if (poly == 2) return launch_nt<2, 0xA, 0>(st, tm, p);
+  return launch_nt<2, 0x8, 0>(st, tm, p);
 }
 
 int launch_build_block_list(cudaStream_t st, const uint8_t* key_mask, int B, int L, int* blk_list, int* blk_count) {

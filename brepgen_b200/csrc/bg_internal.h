@@ -76,6 +76,7 @@ struct AttnArgs {
   const int* blk_count = nullptr;      // [B]
 };
 int launch_attention(cudaStream_t st, const AttnArgs& a);
+int launch_attention_rowsplit(cudaStream_t st, const AttnArgs& a, int poly);   // attn_rs.cu, L > 128 only
 // builds blk_list/blk_count from key_mask ([B,L]); nkb = ceil(L/128)
 int launch_build_block_list(cudaStream_t st, const uint8_t* key_mask, int B, int L, int* blk_list, int* blk_count);
 

@@ -9,6 +9,7 @@
 //   warp 1  : MMA issuer    (one elected thread: 4 x tcgen05.mma.kind::f16 M128 N=BN K16 per 64-wide k-block)
 //   warp 2  : TMEM allocator (2 x BN fp32 columns: accumulator double buffer -> epilogue overlaps next tile)
 //   warps 4-11: epilogue    (8 warps: TMEM lane quarter = warp % 4, column half = (warp - 4) / 4; tcgen05.ld 32x32b,
+//                            32x32 transpose through shared memory so that all global traffic is row-contiguous;
 //                            residual / row-vector loads issued BEFORE the TMEM wait so their latency overlaps it)
 // Roofline: tensor-bound; 2*M*N*K flop per launch.
 #include "bg_internal.h"
@@ -29,7 +30,9 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual 1 KB alignment
+  static constexpr int XPOSE_PITCH = 33;                                  // floats; +1 keeps both access patterns conflict-free
+  static constexpr int XPOSE_BYTES = 8 * 32 * XPOSE_PITCH * 4;            // one 32x32 fp32 staging tile per epilogue warp
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + XPOSE_BYTES + 1024;  // +1024: manual 1 KB alignment
 };
 
 struct GemmParams {
@@ -136,69 +139,70 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else if (warp >= 4) {
+    // Epilogue.  tcgen05.ld hands each thread one accumulator ROW (32 consecutive columns per chunk); writing that
+    // straight out would make every global instruction touch 32 different rows.  Each warp therefore transposes its
+    // 32x32 chunk through a private shared-memory tile, after which lane == column: every residual / row-vector load and
+    // every store instruction covers one contiguous 128-byte (fp32) or 64-byte (fp16) row segment.
     const int ew = (warp - 4) & 3;            // TMEM lane quarter this warp may access
     const int half = (warp - 4) >> 2;         // column half of the tile
-    const int row_in_tile = ew * 32 + lane;
     constexpr int CHUNKS = BN / 64;           // 32-column chunks per half
+    constexpr int PITCH = C::XPOSE_PITCH;
+    float* xp = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES) + (warp - 4) * 32 * PITCH;
     int acc = 0;
     uint32_t accphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
-      const int row = m_blk * BM + row_in_tile;
-      const bool row_ok = row < p.M;
-      const float* vec = p.rowvec ? p.rowvec + (size_t)(row_ok ? row / p.rows_per_vec : 0) * p.ldv : nullptr;
-      const float* res = p.resid ? p.resid + (size_t)(row_ok ? row : 0) * p.ldr : nullptr;
+      const int row0 = m_blk * BM + ew * 32;                 // first of this warp's 32 rows
       const int colbase = n_blk * BN + half * (BN / 2);
-      // additive terms of the first chunk are fetched before waiting for the accumulator
-      float add[32];
-      auto fetch_add = [&](int col0) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) add[i] = 0.f;
-        if (!row_ok) return;
-        if (res) {
-          const float4* rp = reinterpret_cast<const float4*>(res + col0);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 t = rp[i];
-            add[4 * i] = t.x; add[4 * i + 1] = t.y; add[4 * i + 2] = t.z; add[4 * i + 3] = t.w;
-          }
-        }
-        if (vec) {
-          const float4* vp = reinterpret_cast<const float4*>(vec + col0);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 t = __ldg(vp + i);
-            add[4 * i] += t.x; add[4 * i + 1] += t.y; add[4 * i + 2] += t.z; add[4 * i + 3] += t.w;
-          }
-        }
-        if (p.bias) {
-          const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 t = __ldg(bp + i);
-            add[4 * i] += t.x; add[4 * i + 1] += t.y; add[4 * i + 2] += t.z; add[4 * i + 3] += t.w;
-          }
-        }
-      };
-      fetch_add(colbase);
       mbar_wait(&tfull[acc], accphase);
       tc_fence_after();
 #pragma unroll 1
       for (int c = 0; c < CHUNKS; ++c) {
+        const int col0 = colbase + c * 32;
+        const int col = col0 + lane;
+        // additive terms in the transposed (lane == column) layout: issue the loads before touching TMEM
+        const float bias = p.bias ? __ldg(p.bias + col) : 0.f;
+        float add[32];
+        if (p.resid && !p.out_f16) {
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) {
+            const int row = row0 + rr;
+            add[rr] = row < p.M ? p.resid[(size_t)row * p.ldr + col] : 0.f;
+          }
+        } else {
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) add[rr] = 0.f;
+        }
+        if (p.rowvec && !p.out_f16) {
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) {
+            const int row = row0 + rr;
+            if (row < p.M) add[rr] += __ldg(p.rowvec + (size_t)(row / p.rows_per_vec) * p.ldv + col);
+          }
+        }
         uint32_t r[32];
         tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN + half * (BN / 2) + c * 32, r);
         tmem_ld_wait();
-        float v[32];
+        if (p.out_f16) {
+          // fp16 outputs (bias / ReLU only): 64 contiguous bytes per thread, written directly -- the shared-memory
+          // transpose would compete with the MMA operand reads (96 B/clk of the 128 B/clk smem bandwidth) for no gain
+          const int row = row0 + lane;
+          if (row < p.M) {
+            float v[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + add[i];
-        const int col0 = colbase + c * 32;
-        if (c + 1 < CHUNKS) fetch_add(col0 + 32);     // next chunk's loads are in flight while this one is stored
-        if (row_ok) {
-          if (p.relu) {
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+            if (p.bias) {
+              const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-          }
-          if (p.out_f16) {
+              for (int i = 0; i < 8; ++i) {
+                const float4 t = __ldg(bp + i);
+                v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+              }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+            }
             uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + (size_t)row * p.ldo + col0);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -213,10 +217,21 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               u.w = *reinterpret_cast<uint32_t*>(&h3);
               op[i] = u;
             }
-          } else {
-            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)row * p.ldo + col0);
+          }
+          continue;
+        }
+        __syncwarp();                                        // previous chunk's reads of xp are done
 #pragma unroll
-            for (int i = 0; i < 8; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        for (int i = 0; i < 32; ++i) xp[lane * PITCH + i] = __uint_as_float(r[i]);
+        __syncwarp();
+        {
+          float* ob = reinterpret_cast<float*>(p.out);
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) {
+            float v = xp[rr * PITCH + lane] + bias + add[rr];
+            if (p.relu) v = fmaxf(v, 0.f);
+            const int row = row0 + rr;
+            if (row < p.M) ob[(size_t)row * p.ldo + col] = v;
           }
         }
       }
@@ -260,6 +275,7 @@ int launch_gemm_f16(cudaStream_t st, const __half* A, int lda, const __half* W, 
   BG_REQUIRE((reinterpret_cast<uintptr_t>(ep.out) & 15) == 0, "gemm: output must be 16-byte aligned");
   BG_REQUIRE(ep.resid == nullptr || (ep.ldr % 4 == 0 && !ep.out_f16 ? true : ep.ldr % 4 == 0), "gemm: resid pitch");
   BG_REQUIRE(ep.rowvec == nullptr || (ep.rows_per_vec > 0 && ep.ldv % 4 == 0), "gemm: rowvec");
+  BG_REQUIRE(!ep.out_f16 || (ep.resid == nullptr && ep.rowvec == nullptr), "gemm: fp16 output supports bias / ReLU only");
   const int bn = (N % 256 == 0) ? 256 : 128;
   CUtensorMap tmA, tmB;
   const int a_cols = ep.a_kwrap > 0 ? ep.a_kwrap : K;
