@@ -313,9 +313,15 @@ def main():
     fl_attn = B * 3072.0 * L * L
     ach = fl_attn / (ms_attn / 1e3) / 1e12
     del qkv, ao
+    traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape (ncu --set full capture)
+    tp = os.path.join(ROOT, "profiles", "attn_traffic.json")
+    if os.path.exists(tp):
+        tj = json.load(open(tp))
+        if tj.get("B") == B and tj.get("L") == L:
+            traffic = tj["dram_bytes_per_launch"]
     roofline = {"bound": "tensor", "kernel": "attn_kernel<2> (tcgen05 flash attention, B=%d L=%d)" % (B, L),
                 "achieved": ach, "peak": burst, "unit": "TFLOP/s", "frac": ach / burst, "peak_source": f"bf16_tflops burst, {src}",
-                "traffic": None, "ms_per_launch": ms_attn, "flop_per_launch": fl_attn}
+                "traffic": traffic, "ms_per_launch": ms_attn, "flop_per_launch": fl_attn}
     flops_brep = cascade_flops_per_brep(S0, S, E)
     whole = {"algorithmic_tflop_per_brep": flops_brep / 1e12, "achieved_tflops_per_gpu": value / world * flops_brep / 1e12,
              "frac_of_sustained_peak": value / world * flops_brep / 1e12 / sustained}

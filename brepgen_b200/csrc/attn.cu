@@ -452,7 +452,12 @@ int launch_attention(cudaStream_t st, const AttnArgs& a) {
   p.out = a.out; p.ldo = a.ldo; p.B = a.B; p.L = a.L; p.nkb = (a.L + 127) / 128;
   p.key_mask = a.key_mask; p.blk_list = a.blk_list; p.blk_count = a.blk_count;
   p.scale_log2 = 1.4426950408889634f / 8.0f;
-  if (a.L <= 128) return launch_nt<1, 0, 0>(st, tm, p);
+  static int nt1 = -1;                  // BG_ATTN_NT1 = 1: one query tile per CTA, two CTAs per SM, for every L
+  if (nt1 < 0) {
+    const char* e = getenv("BG_ATTN_NT1");
+    nt1 = e ? atoi(e) : 0;
+  }
+  if (a.L <= 128 || nt1) return launch_nt<1, 0, 0>(st, tm, p);
   static int poly = -1;                 // BG_ATTN_POLY = 0 | 1 (25 % of the exponentials) | 2 (50 %); tuning knob
   if (poly < 0) {
     const char* e = getenv("BG_ATTN_POLY");
