@@ -206,6 +206,8 @@ def main():
     dev = torch.device("cuda", local)
     dist = None
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the single JSON line
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 

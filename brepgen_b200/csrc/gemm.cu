@@ -12,10 +12,15 @@
 //                            32x32 transpose through shared memory so that all global traffic is row-contiguous;
 //                            residual / row-vector loads issued BEFORE the TMEM wait so their latency overlaps it)
 // Roofline: tensor-bound; 2*M*N*K flop per launch.
+#include <stdlib.h>
+
 #include "bg_internal.h"
+#include "gemm_epilogue.cuh"
 #include "ptx.cuh"
 
 namespace bg {
+
+int launch_gemm2_f16(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p);   // gemm2.cu
 
 namespace {
 
@@ -30,24 +35,9 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int XPOSE_PITCH = 33;                                  // floats; +1 keeps both access patterns conflict-free
+  static constexpr int XPOSE_PITCH = GEMM_XPOSE_PITCH;
   static constexpr int XPOSE_BYTES = 8 * 32 * XPOSE_PITCH * 4;            // one 32x32 fp32 staging tile per epilogue warp
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + XPOSE_BYTES + 1024;  // +1024: manual 1 KB alignment
-};
-
-struct GemmParams {
-  int M, N, K;
-  int a_kwrap;   // 0, or the K period of A: A column = k % a_kwrap (K-concatenated weights [W_hi | W_lo] reuse A)
-  void* out;
-  int ldo;
-  int out_f16;
-  int relu;
-  const float* bias;
-  const float* resid;
-  int ldr;
-  const float* rowvec;
-  int rows_per_vec;
-  int ldv;
 };
 
 template <int BN>
@@ -146,7 +136,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int ew = (warp - 4) & 3;            // TMEM lane quarter this warp may access
     const int half = (warp - 4) >> 2;         // column half of the tile
     constexpr int CHUNKS = BN / 64;           // 32-column chunks per half
-    constexpr int PITCH = C::XPOSE_PITCH;
+    constexpr int PITCH = GEMM_XPOSE_PITCH;
     float* xp = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES) + (warp - 4) * 32 * PITCH;
     int acc = 0;
     uint32_t accphase = 0;
@@ -156,85 +146,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int colbase = n_blk * BN + half * (BN / 2);
       mbar_wait(&tfull[acc], accphase);
       tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < CHUNKS; ++c) {
-        const int col0 = colbase + c * 32;
-        const int col = col0 + lane;
-        // additive terms in the transposed (lane == column) layout: issue the loads before touching TMEM
-        const float bias = p.bias ? __ldg(p.bias + col) : 0.f;
-        float add[32];
-        if (p.resid && !p.out_f16) {
-#pragma unroll
-          for (int rr = 0; rr < 32; ++rr) {
-            const int row = row0 + rr;
-            add[rr] = row < p.M ? p.resid[(size_t)row * p.ldr + col] : 0.f;
-          }
-        } else {
-#pragma unroll
-          for (int rr = 0; rr < 32; ++rr) add[rr] = 0.f;
-        }
-        if (p.rowvec && !p.out_f16) {
-#pragma unroll
-          for (int rr = 0; rr < 32; ++rr) {
-            const int row = row0 + rr;
-            if (row < p.M) add[rr] += __ldg(p.rowvec + (size_t)(row / p.rows_per_vec) * p.ldv + col);
-          }
-        }
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN + half * (BN / 2) + c * 32, r);
-        tmem_ld_wait();
-        if (p.out_f16) {
-          // fp16 outputs (bias / ReLU only): 64 contiguous bytes per thread, written directly -- the shared-memory
-          // transpose would compete with the MMA operand reads (96 B/clk of the 128 B/clk smem bandwidth) for no gain
-          const int row = row0 + lane;
-          if (row < p.M) {
-            float v[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-            if (p.bias) {
-              const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float4 t = __ldg(bp + i);
-                v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
-              }
-            }
-            if (p.relu) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-            }
-            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + (size_t)row * p.ldo + col0);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              __half2 h0 = __floats2half2_rn(v[8 * i], v[8 * i + 1]);
-              __half2 h1 = __floats2half2_rn(v[8 * i + 2], v[8 * i + 3]);
-              __half2 h2 = __floats2half2_rn(v[8 * i + 4], v[8 * i + 5]);
-              __half2 h3 = __floats2half2_rn(v[8 * i + 6], v[8 * i + 7]);
-              uint4 u;
-              u.x = *reinterpret_cast<uint32_t*>(&h0);
-              u.y = *reinterpret_cast<uint32_t*>(&h1);
-              u.z = *reinterpret_cast<uint32_t*>(&h2);
-              u.w = *reinterpret_cast<uint32_t*>(&h3);
-              op[i] = u;
-            }
-          }
-          continue;
-        }
-        __syncwarp();                                        // previous chunk's reads of xp are done
-#pragma unroll
-        for (int i = 0; i < 32; ++i) xp[lane * PITCH + i] = __uint_as_float(r[i]);
-        __syncwarp();
-        {
-          float* ob = reinterpret_cast<float*>(p.out);
-#pragma unroll
-          for (int rr = 0; rr < 32; ++rr) {
-            float v = xp[rr * PITCH + lane] + bias + add[rr];
-            if (p.relu) v = fmaxf(v, 0.f);
-            const int row = row0 + rr;
-            if (row < p.M) ob[(size_t)row * p.ldo + col] = v;
-          }
-        }
-      }
+      gemm_epilogue_tile<CHUNKS>(p, tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN + half * (BN / 2), row0, colbase, xp, lane);
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
       acc ^= 1;
@@ -277,16 +189,23 @@ int launch_gemm_f16(cudaStream_t st, const __half* A, int lda, const __half* W, 
   BG_REQUIRE(ep.rowvec == nullptr || (ep.rows_per_vec > 0 && ep.ldv % 4 == 0), "gemm: rowvec");
   BG_REQUIRE(!ep.out_f16 || (ep.resid == nullptr && ep.rowvec == nullptr), "gemm: fp16 output supports bias / ReLU only");
   const int bn = (N % 256 == 0) ? 256 : 128;
+  static int two_cta = -1;              // CTA-pair kernel (gemm2.cu) for N % 256 == 0; BG_GEMM_2CTA=0 selects the 1-CTA kernel
+  if (two_cta < 0) {
+    const char* e = getenv("BG_GEMM_2CTA");
+    two_cta = e ? atoi(e) : 1;
+  }
+  const bool use2 = two_cta && bn == 256;
   CUtensorMap tmA, tmB;
   const int a_cols = ep.a_kwrap > 0 ? ep.a_kwrap : K;
   BG_REQUIRE(ep.a_kwrap == 0 || (ep.a_kwrap % BK == 0 && ep.a_kwrap <= K), "gemm: a_kwrap must be a multiple of 64");
   BG_TRY(make_tmap_2d_f16(&tmA, A, (uint64_t)M, (uint64_t)a_cols, (uint64_t)lda, BM));
-  BG_TRY(make_tmap_2d_f16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)bn));
+  BG_TRY(make_tmap_2d_f16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, use2 ? 128u : (uint32_t)bn));
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.a_kwrap = ep.a_kwrap;
   p.out = ep.out; p.ldo = ep.ldo; p.out_f16 = ep.out_f16; p.relu = ep.relu;
   p.bias = ep.bias; p.resid = ep.resid; p.ldr = ep.ldr;
   p.rowvec = ep.rowvec; p.rows_per_vec = ep.rows_per_vec; p.ldv = ep.ldv;
+  if (use2) return launch_gemm2_f16(st, tmA, tmB, p);
   return bn == 256 ? launch_bn<256>(st, tmA, tmB, p) : launch_bn<128>(st, tmA, tmB, p);
 }
 

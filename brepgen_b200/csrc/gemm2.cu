@@ -1,0 +1,204 @@
+// 2-CTA (cta_group::2) variant of the tcgen05 GEMM of gemm.cu:  out[M,N] = epi( A[M,K] * W[N,K]^T ).
+//
+// A CTA pair (thread-block cluster of 2, same TPC) computes one 256 x 256 tile: each CTA owns 128 rows of M (its own A
+// tile and its own 128 x 256 fp32 accumulator in TMEM) and loads only HALF of the 256 weight rows; the leader CTA's single
+// MMA thread issues tcgen05.mma.cta_group::2 (M = 256, N = 256, K = 16), which reads A from both CTAs' shared memory and
+// the two halves of B from the two CTAs.  Per CTA and 64-wide k-block this moves 16 KB (A) + 16 KB (B/2) instead of
+// 16 + 32 KB through L2 -> TMA -> smem -> tensor core, which is what caps the 1-CTA kernel at ~75 % tensor-pipe activity.
+//
+//   warp 0 (both CTAs): TMA producer (cp.async.bulk.tensor ... .cta_group::2, completion bytes land on the LEADER's
+//                       full barrier); waits on its own CTA's empty barrier
+//   warp 1 (leader)   : MMA issuer; tcgen05.commit ... multicast::cluster arrives on the empty / tmem-full barriers of
+//                       BOTH CTAs
+//   warp 2 (both)     : TMEM allocator (tcgen05.alloc.cta_group::2, 512 columns: accumulator double buffer)
+//   warps 4-11 (both) : epilogue (gemm_epilogue.cuh); all 512 epilogue threads of the pair arrive on the leader's
+//                       tmem-empty barrier (the peer through a cluster-mapped address)
+#include "bg_internal.h"
+#include "gemm_epilogue.cuh"
+#include "ptx.cuh"
+
+namespace bg {
+
+namespace {
+
+constexpr int BM_CTA = 128;     // rows per CTA; the pair covers 256
+constexpr int BN = 256;
+constexpr int BK = 64;
+constexpr int STAGES = 6;
+constexpr int A_BYTES = BM_CTA * BK * 2;
+constexpr int B_BYTES = (BN / 2) * BK * 2;
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;            // 32 KB per CTA
+constexpr int BAR_BYTES = 256;
+constexpr int XPOSE_BYTES = 8 * 32 * GEMM_XPOSE_PITCH * 4;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + XPOSE_BYTES + 1024;
+constexpr int TMEM_COLS = 512;
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;               // shared::cluster address of the same offset in the even (leader) CTA
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_ss_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {     // arrives on `bar` (same offset) in both CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);          // leader: its own arrive.expect_tx; the bytes of both CTAs complete on it
+      mbar_init(&empty[i], 1);         // one multicast tcgen05.commit per phase
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 512);      // leader: 256 epilogue threads of each CTA
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_m = (p.M + 2 * BM_CTA - 1) / (2 * BM_CTA);
+  const int num_n = p.N / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_k = p.K / BK;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m_blk = tile / num_n, n_blk = tile % num_n;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * STAGE_BYTES;
+          uint8_t* sB = sA + A_BYTES;
+          const uint32_t leader_full = smem_u32(&full[stage]) & PEER_MASK;
+          if (leader) mbar_arrive_expect_tx(&full[stage], 2 * STAGE_BYTES);
+          const int ka = p.a_kwrap ? (kb * BK) % p.a_kwrap : kb * BK;
+          tma_load_2d_2sm(sA, &tmA, leader_full, ka, m_blk * 2 * BM_CTA + (int)rank * BM_CTA);
+          tma_load_2d_2sm(sB, &tmB, leader_full, kb * BK, n_blk * BN + (int)rank * (BN / 2));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && elect_one()) {
+      constexpr uint32_t idesc = make_idesc_f16(2 * BM_CTA, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t accphase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        mbar_wait(&tempty[acc], accphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_f16_ss_2cta(d_tmem, make_sw128_desc(a_addr + k * 32), make_sw128_desc(b_addr + k * 32), idesc,
+                             (kb | k) != 0 ? 1u : 0u);
+          umma_commit_2cta(&empty[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2cta(&tfull[acc]);
+        acc ^= 1;
+        if (acc == 0) accphase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    const int ew = (warp - 4) & 3;
+    const int half = (warp - 4) >> 2;
+    constexpr int CHUNKS = BN / 64;
+    float* xp = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + BAR_BYTES) + (warp - 4) * 32 * GEMM_XPOSE_PITCH;
+    int acc = 0;
+    uint32_t accphase = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      const int row0 = m_blk * 2 * BM_CTA + (int)rank * BM_CTA + ew * 32;
+      const int colbase = n_blk * BN + half * (BN / 2);
+      mbar_wait(&tfull[acc], accphase);
+      tc_fence_after();
+      gemm_epilogue_tile<CHUNKS>(p, tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN + half * (BN / 2), row0, colbase, xp, lane);
+      tc_fence_before();
+      if (leader) mbar_arrive(&tempty[acc]);
+      else mbar_arrive_cluster(&tempty[acc], 0);
+      acc ^= 1;
+      if (acc == 0) accphase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();       // the peer may still be signalling / reading this CTA's barriers and TMEM until here
+  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+}
+
+}  // namespace
+
+// N % 256 == 0 path of launch_gemm_f16 when BG_GEMM_2CTA != 0
+int launch_gemm2_f16(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p) {
+  static bool configured = false;
+  if (!configured) {
+    BG_CUDA(cudaFuncSetAttribute(gemm2_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    configured = true;
+  }
+  const int num_tiles = ((p.M + 255) / 256) * (p.N / BN);
+  const int max_clusters = num_sms() / 2;
+  const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
+  gemm2_f16_kernel<<<2 * clusters, 384, SMEM_BYTES, st>>>(tmA, tmB, p);
+  return check_launch("gemm2_f16_kernel launch");
+}
+
+}  // namespace bg
