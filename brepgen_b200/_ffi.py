@@ -37,6 +37,8 @@ SIGNATURES = {
     "bg_vae_destroy": (None, [vp]),
     "bg_vae_workspace_bytes": (sz, [vp, i32]),
     "bg_vae_decode": (i32, [vp, vp, i32, vp, vp, sz, vp]),
+    "bg_vae_decode_hw": (i32, [vp, vp, i32, i32, vp, vp, sz, vp]),
+    "bg_vae_encode": (i32, [vp, vp, i32, i32, vp, vp, sz, vp]),
     "bg_ddpm_step": (i32, [vp, vp, f32, vp, vp, vp, u64, u64, i64, f32, f32, f32, f32, f32, f32, vp]),
     "bg_pndm_step": (i32, [vp, vp, i64, f32, f32, vp, f32, vp, f32, vp, f32, vp, f32, vp]),
     "bg_axpby": (i32, [vp, f32, vp, f32, vp, i64, vp]),

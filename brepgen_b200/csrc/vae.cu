@@ -82,9 +82,12 @@ __global__ void postquant_kernel(const float* __restrict__ z, const float* __res
 }
 
 // in (N, H, W, C) fp16 -> A (N*Ho*Wo, Kpad) fp16, 3x3 pad 1 on the (optionally nearest-2x upsampled) image
+// stride 1 / pad_lo 1: the usual 3x3 pad-1 convolution; stride 2 / pad_lo 0: diffusers Downsample2D(padding=0), i.e.
+// zero padding on the right / bottom only.  Hs x Ws = upsampled source extent, Ho x Wo = output extent.
 __global__ void im2col2d_kernel(const __half* __restrict__ in, int ldin, __half* __restrict__ A, int ldA, int H, int W, int C,
-                                int up, int Kpad, size_t total_vec, int vec) {
-  const int Ho = H * up, Wo = W * up;
+                                int up, int stride, int pad_lo, int Kpad, size_t total_vec, int vec) {
+  const int Hs = H * up, Ws = W * up;
+  const int Ho = Hs / stride, Wo = Ws / stride;
   const int kvec = Kpad / vec;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (size_t)gridDim.x * blockDim.x) {
     const size_t row = i / kvec;
@@ -96,8 +99,8 @@ __global__ void im2col2d_kernel(const __half* __restrict__ in, int ldin, __half*
       uint4 v = make_uint4(0, 0, 0, 0);
       if (k < 9 * C) {
         const int tap = k / C, c = k % C;
-        const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
-        if (yy >= 0 && yy < Ho && xx >= 0 && xx < Wo)
+        const int yy = y * stride + tap / 3 - pad_lo, xx = x * stride + tap % 3 - pad_lo;
+        if (yy >= 0 && yy < Hs && xx >= 0 && xx < Ws)
           v = *reinterpret_cast<const uint4*>(in + ((n * H + yy / up) * W + xx / up) * ldin + c);
       }
       *reinterpret_cast<uint4*>(dst) = v;
@@ -105,8 +108,8 @@ __global__ void im2col2d_kernel(const __half* __restrict__ in, int ldin, __half*
       __half v = __float2half_rn(0.f);
       if (k < 9 * C) {
         const int tap = k / C, c = k % C;
-        const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
-        if (yy >= 0 && yy < Ho && xx >= 0 && xx < Wo) v = in[((n * H + yy / up) * W + xx / up) * ldin + c];
+        const int yy = y * stride + tap / 3 - pad_lo, xx = x * stride + tap % 3 - pad_lo;
+        if (yy >= 0 && yy < Hs && xx >= 0 && xx < Ws) v = in[((n * H + yy / up) * W + xx / up) * ldin + c];
       }
       *dst = v;
     }
@@ -263,6 +266,39 @@ __global__ void cubic_up1d_kernel(const float* __restrict__ x, float* __restrict
   }
 }
 
+// diffusers Downsample1d("cubic"): reflect pad 3, depthwise conv1d stride 2.  x (N,L,C) -> (N,L/2,C)
+__global__ void cubic_down1d_kernel(const float* __restrict__ x, float* __restrict__ y, int L, int C, const float* __restrict__ kern,
+                                    size_t total) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int o = (int)((i / C) % (L / 2));
+    const size_t n = i / ((size_t)C * (L / 2));
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      int src = 2 * o + k - 3;
+      if (src < 0) src = -src;
+      if (src >= L) src = 2 * (L - 1) - src;
+      acc = fmaf(x[(n * L + src) * C + c], kern[k], acc);
+    }
+    y[i] = acc;
+  }
+}
+
+// encoder tail: h (N*P, ld) fp32 holds the 6 moment channels of conv_out; mode = first 3 channels of quant_conv(h).
+// out (N, 3, P) fp32
+__global__ void quant_mode_kernel(const float* __restrict__ h, int ld, const float* __restrict__ wq, const float* __restrict__ bq,
+                                  float* __restrict__ out, int N, int P) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * 3 * P) return;
+  const int p = i % P, co = (i / P) % 3, n = i / (3 * P);
+  const float* hr = h + ((size_t)n * P + p) * ld;
+  float acc = bq[co];
+#pragma unroll
+  for (int ci = 0; ci < 6; ++ci) acc = fmaf(wq[co * 6 + ci], hr[ci], acc);
+  out[i] = acc;
+}
+
 // conv_out result (N*P, ld) fp32 -> out (N, 3, P) fp32 (first three channels)
 __global__ void slice_out_kernel(const float* __restrict__ h, int ld, float* __restrict__ out, int N, int P) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -306,7 +342,7 @@ struct Attn {
 using namespace bg;
 
 struct BgVae {
-  int kind = 0;                 // 0 surface (2-D), 1 edge (1-D)
+  int kind = 0;                 // 0 surface decoder, 1 edge decoder, 2 surface encoder, 3 edge encoder
   char* arena = nullptr;
   size_t arena_bytes = 0;
   float *pq_w = nullptr, *pq_b = nullptr, *up_kernel = nullptr;
@@ -321,6 +357,11 @@ struct BgVae {
   Res1d e_mid[6];
   Attn e_attn[6];
   Res1d e_up[3][3];
+  // encoders (kind 2 surface, 3 edge): conv_in / conv_out / norm_out / mid blocks reuse the members above
+  Res2d s_down[4][2];
+  Conv s_downconv[3];
+  Res1d e_down[3][3];
+  float *q_w = nullptr, *q_b = nullptr, *down_kernel = nullptr;
 };
 
 namespace {
@@ -411,7 +452,10 @@ struct VPacker {
   }
 };
 
+int pack_encoder(BgVae* m, VPacker& pk);
+
 int pack_vae(BgVae* m, VPacker& pk) {
+  if (m->kind >= 2) return pack_encoder(m, pk);
   const std::string d = "decoder.";
   const int taps_in = m->kind == 0 ? 9 : 3;
   m->pq_w = pk.copy("post_quant_conv.weight", 9);
@@ -475,6 +519,78 @@ int pack_vae(BgVae* m, VPacker& pk) {
   return pk.err;
 }
 
+int pack_encoder(BgVae* m, VPacker& pk) {
+  const std::string e = "encoder.";
+  const bool surf = m->kind == 2;
+  // the "post-quant" slot holds the identity: the input image goes through the same fp32 -> [hi | lo] fp16 kernel
+  m->pq_w = pk.zeros(9);
+  m->pq_b = pk.zeros(3);
+  if (!pk.dry && !pk.err) {
+    const float ident[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    pk.err = check_cuda(cudaMemcpyAsync(m->pq_w, ident, sizeof(ident), cudaMemcpyHostToDevice, pk.st), "copy identity");
+    if (!pk.err) pk.err = check_cuda(cudaStreamSynchronize(pk.st), "sync");   // `ident` lives on this stack frame
+  }
+  m->conv_in = pk.conv(e + "conv_in", 128, 3, surf ? 9 : 3);
+  if (surf) {
+    auto res2d = [&](const std::string& n, int cin, int cout) {
+      Res2d r;
+      r.n1 = pk.norm(n + ".norm1", cin);
+      r.c1 = pk.conv(n + ".conv1", cout, cin, 9);
+      r.n2 = pk.norm(n + ".norm2", cout);
+      r.c2 = pk.conv(n + ".conv2", cout, cout, 9);
+      r.has_sc = cin != cout;
+      if (r.has_sc) r.sc = pk.conv(n + ".conv_shortcut", cout, cin, 1);
+      return r;
+    };
+    const int chans[4][2] = {{128, 128}, {128, 256}, {256, 512}, {512, 512}};
+    for (int i = 0; i < 4; ++i) {
+      for (int j = 0; j < 2; ++j)
+        m->s_down[i][j] = res2d(e + "down_blocks." + std::to_string(i) + ".resnets." + std::to_string(j),
+                                j == 0 ? chans[i][0] : chans[i][1], chans[i][1]);
+      if (i < 3) m->s_downconv[i] = pk.conv(e + "down_blocks." + std::to_string(i) + ".downsamplers.0.conv", chans[i][1], chans[i][1], 9);
+    }
+    m->s_mid[0] = res2d(e + "mid_block.resnets.0", 512, 512);
+    const std::string a = e + "mid_block.attentions.0";
+    m->s_attn.gn = pk.norm(a + ".group_norm", 512);
+    m->s_attn.qkv = pk.qkv(a, "to_q", "to_k", "to_v", 512);
+    m->s_attn.proj = pk.conv(a + ".to_out.0", 512, 512, 1);
+    m->s_mid[1] = res2d(e + "mid_block.resnets.1", 512, 512);
+    m->norm_out = pk.norm(e + "conv_norm_out", 512);
+    m->conv_out = pk.conv(e + "conv_out", 6, 512, 9, true, 128);
+  } else {
+    auto res1d = [&](const std::string& n, int cin, int cmid, int cout) {
+      Res1d r;
+      r.has_skip = cin != cout;
+      if (r.has_skip) r.skip = pk.conv(n + ".conv_skip", cout, cin, 1, false);
+      r.c1 = pk.conv(n + ".conv_1", cmid, cin, 5);
+      r.n1 = pk.norm(n + ".group_norm_1", cmid);
+      r.c2 = pk.conv(n + ".conv_2", cout, cmid, 5);
+      r.n2 = pk.norm(n + ".group_norm_2", cout);
+      return r;
+    };
+    const int chans[3][2] = {{128, 128}, {128, 256}, {256, 512}};
+    for (int i = 0; i < 3; ++i) {
+      const std::string b = e + "down_blocks." + std::to_string(i);
+      m->e_down[i][0] = res1d(b + ".resnets.0", chans[i][0], chans[i][1], chans[i][1]);
+      m->e_down[i][1] = res1d(b + ".resnets.1", chans[i][1], chans[i][1], chans[i][1]);
+      m->e_down[i][2] = res1d(b + ".resnets.2", chans[i][1], chans[i][1], chans[i][1]);
+    }
+    m->down_kernel = pk.copy(e + "down_blocks.0.down.kernel", 8);
+    for (int i = 0; i < 6; ++i) m->e_mid[i] = res1d(e + "mid_block.resnets." + std::to_string(i), 512, 512, 512);
+    for (int i = 0; i < 6; ++i) {
+      const std::string a = e + "mid_block.attentions." + std::to_string(i);
+      m->e_attn[i].gn = pk.norm(a + ".group_norm", 512);
+      m->e_attn[i].qkv = pk.qkv(a, "query", "key", "value", 512);
+      m->e_attn[i].proj = pk.conv(a + ".proj_attn", 512, 512, 1);
+    }
+    m->norm_out = pk.norm(e + "conv_norm_out", 512);
+    m->conv_out = pk.conv(e + "conv_out", 6, 512, 3, true, 128);
+  }
+  m->q_w = pk.copy("quant_conv.weight", 36);
+  m->q_b = pk.copy("quant_conv.bias", 6);
+  return pk.err;
+}
+
 // per-sample buffer sizes (elements)
 struct VaeWs {
   float *X, *H, *S;        // fp32 activations
@@ -482,10 +598,11 @@ struct VaeWs {
   size_t bytes;
 };
 VaeWs carve_vae(char* base, int kind, size_t N) {
-  // maxima over the layer list (positions x channels per sample)
-  const size_t act = kind == 0 ? 32 * 32 * 256 : 32 * 256;                 // largest activation (elements)
-  const size_t col = kind == 0 ? (size_t)32 * 32 * 9 * 256 : (size_t)16 * 5 * 512;   // largest im2col row block
-  const size_t qkv = kind == 0 ? 16 * 2560 : 4 * 2560;                     // qkv (3C) + attention out (2C, hi | lo)
+  // maxima over the layer list (positions x channels per sample) at the largest supported extent (32 x 32 / 32 points)
+  const bool two_d = (kind & 1) == 0;
+  const size_t act = two_d ? 32 * 32 * 256 : 32 * 256;                    // largest activation (elements)
+  const size_t col = two_d ? (size_t)32 * 32 * 9 * 256 : (size_t)16 * 5 * 512;   // largest im2col row block
+  const size_t qkv = two_d ? 16 * 2560 : 4 * 2560;                        // qkv (3C) + attention out (2C, hi | lo)
   size_t off = 0;
   auto take = [&](size_t bytes) {
     char* p = base ? base + off : nullptr;
@@ -531,11 +648,12 @@ int cast_split(const Ctx& c, const float* x, __half* y, int C, size_t rows) {
   cast_split_kernel<<<grid_for(tot), 256, 0, c.st>>>(x, y, C, tot);
   return check_launch("cast_split_kernel launch");
 }
-int im2col2d(const Ctx& c, const __half* in, int H, int W, int C, int up, int kpad) {
+int im2col2d(const Ctx& c, const __half* in, int H, int W, int C, int up, int kpad, int stride = 1) {
   const int vec = (C % 8 == 0) ? 8 : 1;
-  const size_t tot = c.N * (size_t)(H * up) * (W * up) * (kpad / vec);
+  const int pad_lo = stride == 1 ? 1 : 0;
+  const size_t tot = c.N * (size_t)(H * up / stride) * (W * up / stride) * (kpad / vec);
   for (int part = 0; part < 2; ++part) {   // hi plane, then lo plane of the [hi | lo] activation
-    im2col2d_kernel<<<grid_for(tot), 256, 0, c.st>>>(in + part * C, 2 * C, c.w.A + part * kpad, 2 * kpad, H, W, C, up, kpad, tot, vec);
+    im2col2d_kernel<<<grid_for(tot), 256, 0, c.st>>>(in + part * C, 2 * C, c.w.A + part * kpad, 2 * kpad, H, W, C, up, stride, pad_lo, kpad, tot, vec);
     BG_TRY(check_launch("im2col2d_kernel launch"));
   }
   return BG_OK;
@@ -610,7 +728,7 @@ int resconv1d(const Ctx& c, const Res1d& r, float** px, float** pfree, int L) {
 extern "C" {
 
 int bg_vae_create(int kind, const BgNamedTensor* weights, int n_weights, void* stream, BgVae** out) {
-  BG_REQUIRE((kind == 0 || kind == 1) && weights && n_weights > 0 && out, "vae_create: bad arguments");
+  BG_REQUIRE(kind >= 0 && kind <= 3 && weights && n_weights > 0 && out, "vae_create: bad arguments");
   BG_TRY(bg_check_device());
   BgVae* m = new BgVae();
   m->kind = kind;
@@ -646,7 +764,13 @@ size_t bg_vae_workspace_bytes(const BgVae* m, int N) {
 }
 
 int bg_vae_decode(BgVae* m, const float* z, int N, float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  return bg_vae_decode_hw(m, z, N, 4, out, workspace, workspace_bytes, stream);
+}
+
+int bg_vae_decode_hw(BgVae* m, const float* z, int N, int hw, float* out, void* workspace, size_t workspace_bytes, void* stream) {
   BG_REQUIRE(m && z && out && workspace && N > 0, "vae_decode: bad arguments");
+  BG_REQUIRE(m->kind == 0 || m->kind == 1, "vae_decode: handle is not a decoder");
+  BG_REQUIRE(m->kind == 0 ? (hw >= 1 && hw <= 4) : hw == 4, "vae_decode: latent extent must be 1..4 (surface) or 4 (edge)");
   Ctx c;
   c.st = reinterpret_cast<cudaStream_t>(stream);
   c.N = (size_t)N;
@@ -658,19 +782,20 @@ int bg_vae_decode(BgVae* m, const float* z, int N, float* out, void* workspace, 
   float* spare = c.w.S;
 
   if (m->kind == 0) {
-    int H = 4;
-    postquant_kernel<<<(N * 16 + 255) / 256, 256, 0, c.st>>>(z, m->pq_w, m->pq_b, c.w.T, N, 16);
+    int H = hw;
+    const int T = hw * hw;
+    postquant_kernel<<<(N * T + 255) / 256, 256, 0, c.st>>>(z, m->pq_w, m->pq_b, c.w.T, N, T);
     BG_TRY(check_launch("postquant_kernel launch"));
-    BG_TRY(im2col2d(c, c.w.T, 4, 4, 3, 1, m->conv_in.kpad));
-    BG_TRY(gemm(c, c.w.A, m->conv_in, c.N * 16, x, nullptr, nullptr));
-    BG_TRY(resnet2d(c, m->s_mid[0], &x, &spare, 16, 4));
-    {   // single-head attention over the 16 positions (legacy diffusers attention block), residual
-      BG_TRY(groupnorm(c, x, 16, 512, 32, 1e-6f, m->s_attn.gn, 0, nullptr, nullptr, c.w.T));
-      BG_TRY(gemm(c, c.w.T, m->s_attn.qkv, c.N * 16, nullptr, c.w.Q, nullptr));
-      BG_TRY(attention(c, 16, 1, 512, 0.044194173824159216f));   // 1 / sqrt(512)
-      BG_TRY(gemm(c, c.w.Q + c.N * (size_t)16 * 1536, m->s_attn.proj, c.N * 16, x, nullptr, x));
+    BG_TRY(im2col2d(c, c.w.T, hw, hw, 3, 1, m->conv_in.kpad));
+    BG_TRY(gemm(c, c.w.A, m->conv_in, c.N * T, x, nullptr, nullptr));
+    BG_TRY(resnet2d(c, m->s_mid[0], &x, &spare, T, hw));
+    {   // single-head attention over the hw*hw positions (legacy diffusers attention block), residual
+      BG_TRY(groupnorm(c, x, T, 512, 32, 1e-6f, m->s_attn.gn, 0, nullptr, nullptr, c.w.T));
+      BG_TRY(gemm(c, c.w.T, m->s_attn.qkv, c.N * T, nullptr, c.w.Q, nullptr));
+      BG_TRY(attention(c, T, 1, 512, 0.044194173824159216f));   // 1 / sqrt(512)
+      BG_TRY(gemm(c, c.w.Q + c.N * (size_t)T * 1536, m->s_attn.proj, c.N * T, x, nullptr, x));
     }
-    BG_TRY(resnet2d(c, m->s_mid[1], &x, &spare, 16, 4));
+    BG_TRY(resnet2d(c, m->s_mid[1], &x, &spare, T, hw));
     for (int i = 0; i < 4; ++i) {
       for (int j = 0; j < 3; ++j) BG_TRY(resnet2d(c, m->s_up[i][j], &x, &spare, H * H, H));
       if (i < 3) {
@@ -682,10 +807,10 @@ int bg_vae_decode(BgVae* m, const float* z, int N, float* out, void* workspace, 
         float* t = x; x = spare; spare = t;
       }
     }
-    BG_TRY(groupnorm(c, x, 1024, 128, 32, 1e-6f, m->norm_out, 1, nullptr, nullptr, c.w.T));
-    BG_TRY(im2col2d(c, c.w.T, 32, 32, 128, 1, m->conv_out.kpad));
-    BG_TRY(gemm(c, c.w.A, m->conv_out, c.N * 1024, c.w.H, nullptr, nullptr));
-    slice_out_kernel<<<(N * 3 * 1024 + 255) / 256, 256, 0, c.st>>>(c.w.H, 128, out, N, 1024);
+    BG_TRY(groupnorm(c, x, H * H, 128, 32, 1e-6f, m->norm_out, 1, nullptr, nullptr, c.w.T));
+    BG_TRY(im2col2d(c, c.w.T, H, H, 128, 1, m->conv_out.kpad));
+    BG_TRY(gemm(c, c.w.A, m->conv_out, c.N * H * H, c.w.H, nullptr, nullptr));
+    slice_out_kernel<<<(N * 3 * H * H + 255) / 256, 256, 0, c.st>>>(c.w.H, 128, out, N, H * H);
     return check_launch("slice_out_kernel launch");
   }
 
@@ -716,6 +841,81 @@ int bg_vae_decode(BgVae* m, const float* z, int N, float* out, void* workspace, 
   BG_TRY(gemm(c, c.w.A, m->conv_out, c.N * 32, c.w.H, nullptr, nullptr));
   slice_out_kernel<<<(N * 3 * 32 + 255) / 256, 256, 0, c.st>>>(c.w.H, 128, out, N, 32);
   return check_launch("slice_out_kernel launch");
+}
+
+int bg_vae_encode(BgVae* m, const float* xin, int N, int hw, float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  BG_REQUIRE(m && xin && out && workspace && N > 0, "vae_encode: bad arguments");
+  BG_REQUIRE(m->kind == 2 || m->kind == 3, "vae_encode: handle is not an encoder");
+  BG_REQUIRE(m->kind == 2 ? (hw == 8 || hw == 16 || hw == 24 || hw == 32) : hw == 32,
+             "vae_encode: input extent must be 8/16/24/32 (surface) or 32 (edge)");
+  Ctx c;
+  c.st = reinterpret_cast<cudaStream_t>(stream);
+  c.N = (size_t)N;
+  char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
+  c.w = carve_vae(base, m->kind, c.N);
+  if (c.w.bytes + (size_t)(base - reinterpret_cast<char*>(workspace)) > workspace_bytes)
+    return set_error(BG_ERR_WORKSPACE, "vae_encode: workspace too small");
+  float* x = c.w.X;
+  float* spare = c.w.S;
+
+  if (m->kind == 2) {
+    int H = hw;
+    postquant_kernel<<<(N * H * H + 255) / 256, 256, 0, c.st>>>(xin, m->pq_w, m->pq_b, c.w.T, N, H * H);   // identity: cast
+    BG_TRY(check_launch("postquant_kernel launch"));
+    BG_TRY(im2col2d(c, c.w.T, H, H, 3, 1, m->conv_in.kpad));
+    BG_TRY(gemm(c, c.w.A, m->conv_in, c.N * H * H, x, nullptr, nullptr));
+    for (int i = 0; i < 4; ++i) {
+      for (int j = 0; j < 2; ++j) BG_TRY(resnet2d(c, m->s_down[i][j], &x, &spare, H * H, H));
+      if (i < 3) {
+        const Conv& dc = m->s_downconv[i];
+        BG_TRY(cast_split(c, x, c.w.T, dc.cin, c.N * (size_t)H * H));
+        BG_TRY(im2col2d(c, c.w.T, H, H, dc.cin, 1, dc.kpad, 2));
+        H /= 2;
+        BG_TRY(gemm(c, c.w.A, dc, c.N * H * H, spare, nullptr, nullptr));
+        float* t = x; x = spare; spare = t;
+      }
+    }
+    const int T = H * H;
+    BG_TRY(resnet2d(c, m->s_mid[0], &x, &spare, T, H));
+    BG_TRY(groupnorm(c, x, T, 512, 32, 1e-6f, m->s_attn.gn, 0, nullptr, nullptr, c.w.T));
+    BG_TRY(gemm(c, c.w.T, m->s_attn.qkv, c.N * T, nullptr, c.w.Q, nullptr));
+    BG_TRY(attention(c, T, 1, 512, 0.044194173824159216f));
+    BG_TRY(gemm(c, c.w.Q + c.N * (size_t)T * 1536, m->s_attn.proj, c.N * T, x, nullptr, x));
+    BG_TRY(resnet2d(c, m->s_mid[1], &x, &spare, T, H));
+    BG_TRY(groupnorm(c, x, T, 512, 32, 1e-6f, m->norm_out, 1, nullptr, nullptr, c.w.T));
+    BG_TRY(im2col2d(c, c.w.T, H, H, 512, 1, m->conv_out.kpad));
+    BG_TRY(gemm(c, c.w.A, m->conv_out, c.N * T, c.w.H, nullptr, nullptr));
+    quant_mode_kernel<<<(N * 3 * T + 255) / 256, 256, 0, c.st>>>(c.w.H, 128, m->q_w, m->q_b, out, N, T);
+    return check_launch("quant_mode_kernel launch");
+  }
+
+  int L = 32;
+  postquant_kernel<<<(N * L + 255) / 256, 256, 0, c.st>>>(xin, m->pq_w, m->pq_b, c.w.T, N, L);
+  BG_TRY(check_launch("postquant_kernel launch"));
+  BG_TRY(im2col1d(c, c.w.T, L, 3, 3, m->conv_in.kpad));
+  BG_TRY(gemm(c, c.w.A, m->conv_in, c.N * L, x, nullptr, nullptr));
+  for (int i = 0; i < 3; ++i) {
+    const int C = m->e_down[i][0].c1.cin;
+    const size_t tot = c.N * (size_t)(L / 2) * C;
+    cubic_down1d_kernel<<<grid_for(tot), 256, 0, c.st>>>(x, spare, L, C, m->down_kernel, tot);
+    BG_TRY(check_launch("cubic_down1d_kernel launch"));
+    float* t = x; x = spare; spare = t;
+    L /= 2;
+    for (int j = 0; j < 3; ++j) BG_TRY(resconv1d(c, m->e_down[i][j], &x, &spare, L));
+  }
+  for (int i = 0; i < 6; ++i) {
+    BG_TRY(resconv1d(c, m->e_mid[i], &x, &spare, 4));
+    const Attn& a = m->e_attn[i];
+    BG_TRY(groupnorm(c, x, 4, 512, 1, 1e-5f, a.gn, 0, nullptr, nullptr, c.w.T));
+    BG_TRY(gemm(c, c.w.T, a.qkv, c.N * 4, nullptr, c.w.Q, nullptr));
+    BG_TRY(attention(c, 4, 16, 32, 0.17677669529663687f));
+    BG_TRY(gemm(c, c.w.Q + c.N * (size_t)4 * 1536, a.proj, c.N * 4, x, nullptr, x));
+  }
+  BG_TRY(groupnorm(c, x, 4, 512, 32, 1e-6f, m->norm_out, 1, nullptr, nullptr, c.w.T));
+  BG_TRY(im2col1d(c, c.w.T, 4, 512, 3, m->conv_out.kpad));
+  BG_TRY(gemm(c, c.w.A, m->conv_out, c.N * 4, c.w.H, nullptr, nullptr));
+  quant_mode_kernel<<<(N * 3 * 4 + 255) / 256, 256, 0, c.st>>>(c.w.H, 128, m->q_w, m->q_b, out, N, 4);
+  return check_launch("quant_mode_kernel launch");
 }
 
 }  // extern "C"

@@ -147,3 +147,54 @@ def edge_decoder_spec() -> Spec:
 
 CUBIC_UP_KERNEL = [2 * v for v in (-0.01171875, -0.03515625, 0.11328125, 0.43359375, 0.43359375, 0.11328125,
                                    -0.03515625, -0.01171875)]   # diffusers Upsample1d("cubic") buffer (kernel * 2)
+
+
+# ------------------------------------------------------------------------------------------------ VAE encoders
+CUBIC_DOWN_KERNEL = [v / 2 for v in CUBIC_UP_KERNEL]      # diffusers Downsample1d("cubic") buffer (un-doubled taps)
+
+
+def surf_encoder_spec() -> Spec:
+    """AutoencoderKLFastEncode (network.py:861-945) = diffusers 0.27 `Encoder` + quant_conv; block_out_channels
+    [128,256,512,512], layers_per_block 2, double_z (6 output channels), trainer.py:20-30 / SURVEY Appendix A.1."""
+    e = "encoder"
+    out = _conv(f"{e}.conv_in", 128, 3, 3, 3)
+    chans = [(128, 128), (128, 256), (256, 512), (512, 512)]
+    for i, (cin, cout) in enumerate(chans):
+        for j in range(2):
+            out += _resnet2d(f"{e}.down_blocks.{i}.resnets.{j}", cin if j == 0 else cout, cout)
+        if i < 3:
+            out += _conv(f"{e}.down_blocks.{i}.downsamplers.0.conv", cout, cout, 3, 3)
+    out += _resnet2d(f"{e}.mid_block.resnets.0", 512, 512)
+    a = f"{e}.mid_block.attentions.0"
+    out += _norm(f"{a}.group_norm", 512)
+    for n in ("to_q", "to_k", "to_v"):
+        out += [(f"{a}.{n}.weight", (512, 512)), (f"{a}.{n}.bias", (512,))]
+    out += [(f"{a}.to_out.0.weight", (512, 512)), (f"{a}.to_out.0.bias", (512,))]
+    out += _resnet2d(f"{e}.mid_block.resnets.1", 512, 512)
+    out += _norm(f"{e}.conv_norm_out", 512) + _conv(f"{e}.conv_out", 6, 512, 3, 3)
+    out += _conv("quant_conv", 6, 6, 1, 1)
+    return out
+
+
+def edge_encoder_spec() -> Spec:
+    """AutoencoderKL1DFastEncode (network.py:690-783) -> Encoder1D (:86-185): conv_in k3 3->128, three diffusers
+    DownBlock1D (cubic Downsample1d first, then ResConvBlock(in,out,out), (out,out,out), (out,out,out)), the 1-D mid block
+    (6 x ResConvBlock + SelfAttention1d), GroupNorm32 + SiLU + conv_out 512->6, quant_conv."""
+    e = "encoder"
+    out = _conv(f"{e}.conv_in", 128, 3, 3)
+    for i, (cin, cout) in enumerate([(128, 128), (128, 256), (256, 512)]):
+        b = f"{e}.down_blocks.{i}"
+        out += [(f"{b}.down.kernel", (8,))]
+        out += _resconv1d(f"{b}.resnets.0", cin, cout, cout)
+        out += _resconv1d(f"{b}.resnets.1", cout, cout, cout)
+        out += _resconv1d(f"{b}.resnets.2", cout, cout, cout)
+    for i in range(6):
+        out += _resconv1d(f"{e}.mid_block.resnets.{i}", 512, 512, 512)
+    for i in range(6):
+        a = f"{e}.mid_block.attentions.{i}"
+        out += _norm(f"{a}.group_norm", 512)
+        for n in ("query", "key", "value", "proj_attn"):
+            out += [(f"{a}.{n}.weight", (512, 512)), (f"{a}.{n}.bias", (512,))]
+    out += _norm(f"{e}.conv_norm_out", 512) + _conv(f"{e}.conv_out", 6, 512, 3)
+    out += _conv("quant_conv", 6, 6, 1)
+    return out

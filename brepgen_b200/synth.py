@@ -31,6 +31,9 @@ def synth_tensor(key: str, shape: Tuple[int, ...], seed: int = 0) -> torch.Tenso
     if key.endswith("up.kernel"):   # fixed resampling buffer of diffusers Upsample1d("cubic"), not a learnt weight
         from .spec import CUBIC_UP_KERNEL
         return torch.tensor(CUBIC_UP_KERNEL, dtype=torch.float32)
+    if key.endswith("down.kernel"):
+        from .spec import CUBIC_DOWN_KERNEL
+        return torch.tensor(CUBIC_DOWN_KERNEL, dtype=torch.float32)
     if len(shape) >= 2:
         fan_in = 1
         for s in shape[1:]:

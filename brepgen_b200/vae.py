@@ -1,4 +1,5 @@
-"""Drop-in VAE decoders with the reference's constructor kwargs, forward signature and state-dict keys.
+"""Drop-in VAE decoders (and the encoders of BASELINE config 1) with the reference's constructor kwargs, forward
+signature and state-dict keys.
 
     AutoencoderKLFastDecode(**cfg).forward(z)      network.py:948-1040   z (N,3,4,4) -> (N,3,32,32)   cfg sample.py:72-82
     AutoencoderKL1DFastDecode(**cfg).forward(z)    network.py:786-858    z (N,3,4)   -> (N,3,32)      cfg sample.py:86-97
@@ -17,7 +18,8 @@ import torch.nn as nn
 
 from . import _ffi
 from .models import _register_tree
-from .spec import CUBIC_UP_KERNEL, edge_decoder_spec, surf_decoder_spec
+from .spec import (CUBIC_DOWN_KERNEL, CUBIC_UP_KERNEL, edge_decoder_spec, edge_encoder_spec, surf_decoder_spec,
+                   surf_encoder_spec)
 from .synth import synth_state_dict
 
 
@@ -31,14 +33,15 @@ class _Decoder(nn.Module):
             if k in cfg and list(cfg[k]) != list(v):
                 raise NotImplementedError(f"{type(self).__name__}: only {k}={v} (the reference's sample.py config) is built")
         for key, shape in spec:
-            if key.endswith("up.kernel"):
+            if key.endswith(".kernel"):       # fixed resampling taps: a registered buffer, like diffusers' Up/Downsample1d
                 parts = key.split(".")
                 mod = self
                 for p in parts[:-1]:
                     if not hasattr(mod, p):
                         mod.add_module(p, nn.Module())
                     mod = getattr(mod, p)
-                mod.register_buffer("kernel", torch.tensor(CUBIC_UP_KERNEL, dtype=torch.float32))
+                taps = CUBIC_UP_KERNEL if key.endswith("up.kernel") else CUBIC_DOWN_KERNEL
+                mod.register_buffer("kernel", torch.tensor(taps, dtype=torch.float32))
             else:
                 _register_tree(self, key, torch.zeros(shape) if len(shape) == 1 else torch.randn(shape) * 0.02)
         self._handle, self._sig, self._ws = None, None, None
@@ -78,7 +81,12 @@ class _Decoder(nn.Module):
         dev = z.device
         z = z.detach().float().contiguous()
         N = z.shape[0]
-        out = torch.empty((N, 3) + tuple(s * 8 for s in z.shape[2:]), device=dev, dtype=torch.float32)
+        encode = self.kind >= 2
+        hw = z.shape[-1]
+        if z.dim() == 4 and z.shape[2] != z.shape[3]:
+            raise NotImplementedError("only square grids")
+        spatial = tuple((s // 8) if encode else (s * 8) for s in z.shape[2:])
+        out = torch.empty((N, 3) + spatial, device=dev, dtype=torch.float32)
         with torch.cuda.device(dev):
             self._ensure(dev)
             step = min(self.chunk, N)
@@ -87,9 +95,9 @@ class _Decoder(nn.Module):
                 self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
             for lo in range(0, N, step):
                 n = min(step, N - lo)
-                _ffi.check(_ffi.lib().bg_vae_decode(self._handle, z[lo:lo + n].data_ptr(), n, out[lo:lo + n].data_ptr(),
-                                                   self._ws.data_ptr(), self._ws.numel(), _ffi.current_stream()),
-                           "bg_vae_decode")
+                fn = _ffi.lib().bg_vae_encode if encode else _ffi.lib().bg_vae_decode_hw
+                _ffi.check(fn(self._handle, z[lo:lo + n].data_ptr(), n, hw, out[lo:lo + n].data_ptr(), self._ws.data_ptr(),
+                              self._ws.numel(), _ffi.current_stream()), "bg_vae_encode" if encode else "bg_vae_decode")
         return out
 
 
@@ -117,6 +125,34 @@ class AutoencoderKL1DFastDecode(_Decoder):
         if (in_channels, out_channels, layers_per_block, act_fn, latent_channels, norm_num_groups) != (3, 3, 2, "silu", 3, 32):
             raise NotImplementedError("AutoencoderKL1DFastDecode: only the configuration of sample.py:86-97 is built")
         super().__init__(edge_decoder_spec(), dict(block_out_channels=[128, 256, 512]), cfg)
+
+
+class AutoencoderKLFastEncode(_Decoder):
+    """network.py:861-945: forward(x (N,3,H,W)) -> DiagonalGaussianDistribution(quant_conv(encoder(x))).mode()"""
+    kind = 2
+    chunk = 1024
+
+    def __init__(self, in_channels=3, out_channels=3, down_block_types=None, up_block_types=None,
+                 block_out_channels=(128, 256, 512, 512), layers_per_block=2, act_fn="silu", latent_channels=3,
+                 norm_num_groups=32, sample_size=512, **unused):
+        if (in_channels, layers_per_block, act_fn, latent_channels, norm_num_groups) != (3, 2, "silu", 3, 32):
+            raise NotImplementedError("AutoencoderKLFastEncode: only the reference's surface-VAE configuration is built")
+        super().__init__(surf_encoder_spec(), dict(block_out_channels=[128, 256, 512, 512]),
+                         dict(block_out_channels=block_out_channels))
+
+
+class AutoencoderKL1DFastEncode(_Decoder):
+    """network.py:690-783: forward(x (N,3,32)) -> latent mode (N,3,4)"""
+    kind = 3
+    chunk = 32768
+
+    def __init__(self, in_channels=3, out_channels=3, down_block_types=None, up_block_types=None,
+                 block_out_channels=(128, 256, 512), layers_per_block=2, act_fn="silu", latent_channels=3,
+                 norm_num_groups=32, sample_size=512, **unused):
+        if (in_channels, layers_per_block, act_fn, latent_channels, norm_num_groups) != (3, 2, "silu", 3, 32):
+            raise NotImplementedError("AutoencoderKL1DFastEncode: only the reference's edge-VAE configuration is built")
+        super().__init__(edge_encoder_spec(), dict(block_out_channels=[128, 256, 512]),
+                         dict(block_out_channels=block_out_channels))
 
 
 def build_synthetic_decoders(device, seed: int = 2):

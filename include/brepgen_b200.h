@@ -87,10 +87,19 @@ int bg_denoiser_forward(BgDenoiser* m, const BgDenoiserArgs* args, void* workspa
  * sample.py:72-97.  `weights`: the `decoder.*` and `post_quant_conv.*` entries of the checkpoint (extra keys ignored).
  * ------------------------------------------------------------------------------------------------------------- */
 typedef struct BgVae BgVae;
+/* kind: 0 surface decoder, 1 edge decoder, 2 surface encoder, 3 edge encoder */
 int bg_vae_create(int kind, const BgNamedTensor* weights, int n_weights, void* stream, BgVae** out);
 void bg_vae_destroy(BgVae* m);
 size_t bg_vae_workspace_bytes(const BgVae* m, int N);
 int bg_vae_decode(BgVae* m, const float* z, int N, float* out, void* workspace, size_t workspace_bytes, void* stream);
+/* surface decoder with a latent of hw x hw (1..4) positions -> (N,3,8hw,8hw); bg_vae_decode == hw 4 */
+int bg_vae_decode_hw(BgVae* m, const float* z, int N, int hw, float* out, void* workspace, size_t workspace_bytes,
+                     void* stream);
+/* Encoders (BASELINE config 1 round trip): kind 2 = AutoencoderKLFastEncode.forward network.py:927-945,
+ * x (N,3,hw,hw), hw in {8,16,24,32} -> latent mode (N,3,hw/8,hw/8); kind 3 = AutoencoderKL1DFastEncode.forward
+ * network.py:745-783, x (N,3,32) -> (N,3,4).  `weights`: `encoder.*` and `quant_conv.*`. */
+int bg_vae_encode(BgVae* m, const float* x, int N, int hw, float* out, void* workspace, size_t workspace_bytes,
+                  void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Scheduler updates.  Replace diffusers DDPMScheduler.step / PNDMScheduler.step as called at

@@ -46,7 +46,7 @@ def _attn2d(sd: SD, name: str, x):
 
 
 def surf_decode(sd: SD, z: torch.Tensor) -> torch.Tensor:
-    """z (N,3,4,4) -> (N,3,32,32)"""
+    """z (N,3,h,w) -> (N,3,8h,8w); the cascade uses h = w = 4 (sample.py:289)"""
     d = "decoder"
     x = F.conv2d(z, sd["post_quant_conv.weight"], sd["post_quant_conv.bias"])
     x = F.conv2d(x, sd[f"{d}.conv_in.weight"], sd[f"{d}.conv_in.bias"], padding=1)
@@ -111,3 +111,56 @@ def edge_decode(sd: SD, z: torch.Tensor) -> torch.Tensor:
         x = cubic_upsample1d(x, sd[f"{d}.up_blocks.{i}.up.kernel"])
     x = F.silu(_gn(x, sd, f"{d}.conv_norm_out", 32, 1e-6))
     return F.conv1d(x, sd[f"{d}.conv_out.weight"], sd[f"{d}.conv_out.bias"], padding=1)
+
+
+# ------------------------------------------------------------------------------------------------ encoders (config 1)
+# AutoencoderKLFastEncode.forward network.py:927-945 and AutoencoderKL1DFastEncode.forward :745-783 return
+# DiagonalGaussianDistribution(quant_conv(encoder(x))).mode() = the first half of the channels.  PARITY UNPINNED (diffusers).
+def surf_encode(sd: SD, x: torch.Tensor) -> torch.Tensor:
+    """x (N,3,H,W), H and W divisible by 8 -> latent mode (N,3,H/8,W/8)"""
+    e = "encoder"
+    h = F.conv2d(x, sd[f"{e}.conv_in.weight"], sd[f"{e}.conv_in.bias"], padding=1)
+    for i in range(4):
+        for j in range(2):
+            h = _resnet2d(sd, f"{e}.down_blocks.{i}.resnets.{j}", h)
+        if i < 3:   # diffusers Downsample2D(padding=0): pad right/bottom by one, 3x3 stride 2
+            h = F.pad(h, (0, 1, 0, 1), mode="constant", value=0)
+            h = F.conv2d(h, sd[f"{e}.down_blocks.{i}.downsamplers.0.conv.weight"],
+                         sd[f"{e}.down_blocks.{i}.downsamplers.0.conv.bias"], stride=2)
+    h = _resnet2d(sd, f"{e}.mid_block.resnets.0", h)
+    h = _attn2d(sd, f"{e}.mid_block.attentions.0", h)
+    h = _resnet2d(sd, f"{e}.mid_block.resnets.1", h)
+    h = F.silu(_gn(h, sd, f"{e}.conv_norm_out", 32, 1e-6))
+    h = F.conv2d(h, sd[f"{e}.conv_out.weight"], sd[f"{e}.conv_out.bias"], padding=1)
+    moments = F.conv2d(h, sd["quant_conv.weight"], sd["quant_conv.bias"])
+    return moments[:, :3]
+
+
+def cubic_downsample1d(x, kernel):
+    """diffusers Downsample1d('cubic'): reflect pad 3, depthwise conv1d stride 2: L -> L/2"""
+    C = x.shape[1]
+    x = F.pad(x, (3, 3), "reflect")
+    w = x.new_zeros(C, C, kernel.shape[0])
+    idx = torch.arange(C)
+    w[idx, idx] = kernel.to(x)
+    return F.conv1d(x, w, stride=2)
+
+
+def edge_encode(sd: SD, x: torch.Tensor) -> torch.Tensor:
+    """x (N,3,32) -> latent mode (N,3,4)"""
+    e = "encoder"
+    h = F.conv1d(x, sd[f"{e}.conv_in.weight"], sd[f"{e}.conv_in.bias"], padding=1)
+    for i in range(3):
+        h = cubic_downsample1d(h, sd[f"{e}.down_blocks.{i}.down.kernel"])
+        for j in range(3):
+            h = _resconv1d(sd, f"{e}.down_blocks.{i}.resnets.{j}", h)
+    for i in range(6):
+        h = _resconv1d(sd, f"{e}.mid_block.resnets.{i}", h)
+        h = _attn1d(sd, f"{e}.mid_block.attentions.{i}", h)
+    h = F.silu(_gn(h, sd, f"{e}.conv_norm_out", 32, 1e-6))
+    h = F.conv1d(h, sd[f"{e}.conv_out.weight"], sd[f"{e}.conv_out.bias"], padding=1)
+    moments = F.conv1d(h, sd["quant_conv.weight"], sd["quant_conv.bias"])
+    return moments[:, :3]
+
+
+surf_decode_any = surf_decode     # the restated decoder is size-agnostic (convolutions + nearest upsampling)

@@ -69,3 +69,60 @@ def test_cascade_with_decode_shapes():
     out = Cascade(ms, sv, ev).run(cfg)
     assert out["surf_ncs"].shape == (2, 6, 32, 32, 3) and out["edge_ncs"].shape == (2, 6, 4, 32, 3)
     assert torch.isfinite(out["surf_ncs"]).all() and torch.isfinite(out["edge_ncs"]).all()
+
+
+def test_encoders_match_oracle():
+    from brepgen_b200.spec import edge_encoder_spec, surf_encoder_spec
+    from brepgen_b200.vae import AutoencoderKL1DFastEncode, AutoencoderKLFastEncode
+    g = torch.Generator().manual_seed(21)
+    sds, sde = synth_state_dict(surf_encoder_spec(), seed=7), synth_state_dict(edge_encoder_spec(), seed=8)
+    es = AutoencoderKLFastEncode(block_out_channels=[128, 256, 512, 512])
+    es.load_state_dict({**sds, "decoder.conv_in.bias": torch.zeros(512)}, strict=False)
+    ee = AutoencoderKL1DFastEncode(block_out_channels=[128, 256, 512])
+    ee.load_state_dict(sde, strict=False)
+    es, ee = es.cuda().eval(), ee.cuda().eval()
+    for hw in (16, 32):
+        x = torch.rand(3, 3, hw, hw, generator=g) * 2 - 1
+        with torch.no_grad():
+            ref, y = V.surf_encode(sds, x), es(x.cuda()).cpu()
+        assert y.shape == (3, 3, hw // 8, hw // 8)
+        err = rel_l2(y, ref)
+        print(f"surface encoder {hw}x{hw} rel_l2={err:.3e}")
+        assert err < 1e-3, err
+    x = torch.rand(5, 3, 32, generator=g) * 2 - 1
+    with torch.no_grad():
+        ref, y = V.edge_encode(sde, x), ee(x.cuda()).cpu()
+    err = rel_l2(y, ref)
+    print(f"edge encoder rel_l2={err:.3e}")
+    assert y.shape == (5, 3, 4) and err < 1e-3, err
+
+
+def test_config1_roundtrip():
+    """BASELINE.json configs[0]: surface VAE encode -> decode round trip, batch 4 of 16x16x3 grids (and the edge
+    analogue, batch 4 of 32x3), through the drop-in classes vs the oracle, U(-1,1) inputs seed 0."""
+    from brepgen_b200.spec import edge_encoder_spec, surf_encoder_spec
+    from brepgen_b200.vae import (AutoencoderKL1DFastDecode, AutoencoderKL1DFastEncode, AutoencoderKLFastDecode,
+                                  AutoencoderKLFastEncode)
+    g = torch.Generator().manual_seed(0)
+    full_s = {**synth_state_dict(surf_encoder_spec(), 9), **synth_state_dict(surf_decoder_spec(), 9)}   # a "full AE" checkpoint
+    full_e = {**synth_state_dict(edge_encoder_spec(), 9), **synth_state_dict(edge_decoder_spec(), 9)}
+    mods = []
+    for cls, sd in ((AutoencoderKLFastEncode, full_s), (AutoencoderKLFastDecode, full_s),
+                    (AutoencoderKL1DFastEncode, full_e), (AutoencoderKL1DFastDecode, full_e)):
+        m = cls()
+        m.load_state_dict(sd, strict=False)
+        mods.append(m.cuda().eval())
+    es, ds, ee, de = mods
+    x = torch.rand(4, 3, 16, 16, generator=g) * 2 - 1
+    with torch.no_grad():
+        ref = V.surf_decode_any(full_s, V.surf_encode(full_s, x))
+        y = ds(es(x.cuda())).cpu()
+    assert y.shape == (4, 3, 16, 16)
+    e1 = rel_l2(y, ref)
+    xe = torch.rand(4, 3, 32, generator=g) * 2 - 1
+    with torch.no_grad():
+        refe = V.edge_decode(full_e, V.edge_encode(full_e, xe))
+        ye = de(ee(xe.cuda())).cpu()
+    e2 = rel_l2(ye, refe)
+    print(f"config-1 round trip: surface 16x16 rel_l2={e1:.3e}  edge rel_l2={e2:.3e}")
+    assert e1 < 1e-3 and e2 < 1e-3
