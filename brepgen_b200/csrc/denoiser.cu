@@ -44,8 +44,10 @@ const KindDef KINDS[4] = {
 };
 
 struct LayerW {
-  __half *wqkv, *wo, *w1, *w2;   // [N][k*] fp16; k* = K (single) or 2K ([W_hi | W_lo], split-weight GEMM)
-  int kqkv, ko, k1, k2;
+  // [N][k*] fp16; k* = K (single) or 2K ([W_hi | W_lo], split-weight GEMM).  in_proj is packed as two operands: the
+  // q|k rows (their rounding error only perturbs the softmax logits: 1.5e-5 of the output) and the v rows (4.8e-4, split)
+  __half *wqk, *wv, *wo, *w1, *w2;
+  int kqk, kv, ko, k1, k2;
   float *bqkv, *bo, *b1, *b2, *ln1g, *ln1b, *ln2g, *ln2b;
 };
 
@@ -137,7 +139,7 @@ using namespace bg;
 
 struct BgDenoiser {
   int kind = 0, use_cf = 0;
-  int precision = 1;           // 0: plain fp16 operands; 1: + split in/out-proj weights + compensated fc_out; 2: all split
+  int precision = 1;           // 0: plain fp16 operands; 1: + split V / out-proj weights + compensated fc_out; 2: all split
   char* arena = nullptr;       // one device allocation holding every packed tensor
   size_t arena_bytes = 0;
   LayerW layer[NLAYER];
@@ -198,8 +200,9 @@ struct Packer {
     return dst;
   }
   // [N][K] fp32 -> fp16 [N][K] (split == 0) or [N][2K] = [W_hi | W_lo]; returns the packed K through *k_out
-  __half* pack_weight(const std::string& name, int N, int K, bool split, int* k_out) {
-    const float* src = find(name, (int64_t)N * K);
+  __half* pack_weight(const std::string& name, int N, int K, bool split, int* k_out, int row0 = 0, int rows_total = 0) {
+    const float* src = find(name, (int64_t)(rows_total ? rows_total : N) * K);
+    if (src) src += (size_t)row0 * K;
     const int kp = split ? 2 * K : K;
     *k_out = kp;
     __half* dst = take<__half>((size_t)N * kp);
@@ -219,7 +222,8 @@ int pack(BgDenoiser* m, Packer& pk, const float* sincos) {
     const std::string p = "net.layers." + std::to_string(i) + ".";
     LayerW& L = m->layer[i];
     const bool s_attn = m->precision >= 1, s_ff = m->precision >= 2;
-    L.wqkv = pk.pack_weight(p + "self_attn.in_proj_weight", 3 * D, D, s_attn, &L.kqkv);
+    L.wqk = pk.pack_weight(p + "self_attn.in_proj_weight", 2 * D, D, s_ff, &L.kqk, 0, 3 * D);
+    L.wv = pk.pack_weight(p + "self_attn.in_proj_weight", D, D, s_attn, &L.kv, 2 * D, 3 * D);
     L.bqkv = pk.copy_f32(p + "self_attn.in_proj_bias", 3 * D);
     L.wo = pk.pack_weight(p + "self_attn.out_proj.weight", D, D, s_attn, &L.ko);
     L.bo = pk.copy_f32(p + "self_attn.out_proj.bias", D);
@@ -473,8 +477,11 @@ int bg_denoiser_forward(BgDenoiser* m, const BgDenoiserArgs* a, void* workspace,
     {
       GemmEpilogue ep;
       ep.out = w.QKV; ep.ldo = 3 * D; ep.out_f16 = 1; ep.bias = Lw.bqkv;
-      ep.a_kwrap = Lw.kqkv > D ? D : 0;
-      BG_TRY(launch_gemm_f16(st, w.Xn, D, Lw.wqkv, Lw.kqkv, M, 3 * D, Lw.kqkv, ep));
+      ep.a_kwrap = Lw.kqk > D ? D : 0;
+      BG_TRY(launch_gemm_f16(st, w.Xn, D, Lw.wqk, Lw.kqk, M, 2 * D, Lw.kqk, ep));     // q | k
+      ep.out = w.QKV + 2 * D; ep.bias = Lw.bqkv + 2 * D;
+      ep.a_kwrap = Lw.kv > D ? D : 0;
+      BG_TRY(launch_gemm_f16(st, w.Xn, D, Lw.wv, Lw.kv, M, D, Lw.kv, ep));            // v
     }
     {
       AttnArgs at;

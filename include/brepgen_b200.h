@@ -57,8 +57,9 @@ typedef struct {
  * `sincos` may be NULL (table built on device) or a device fp32 [1000][768] copy of network.py:1043 sincos_embedding
  * for t = 0..999.  The weights may be freed after the call returns AND `stream` has been synchronised.
  * precision: 0 = plain fp16 tensor-core operands (error ~1e-3 of the fp32 reference, like the reference's own fp16
- *            autocast path); 1 (default) = in_proj/out_proj weights as fp16 hi+lo pairs and a compensated fc_out tail
- *            (error ~5e-4); 2 = all four encoder weight matrices as hi+lo pairs.  All modes accumulate in fp32 and keep
+ *            autocast path); 1 (default) = the value rows of in_proj and out_proj as fp16 hi+lo pairs and a compensated
+ *            fc_out tail (error ~5e-4; the q / k rows only perturb the softmax logits, 1.5e-5, and stay single);
+ *            2 = all four encoder weight matrices as hi+lo pairs.  All modes accumulate in fp32 and keep
  *            the residual stream, LayerNorm, softmax statistics and the scheduler in fp32. */
 int bg_denoiser_create(int kind, int use_cf, int precision, const BgNamedTensor* weights, int n_weights,
                        const float* sincos, void* stream, BgDenoiser** out);
