@@ -75,7 +75,7 @@ def cascade_flops_per_brep(S0, S, E, steps=1000):
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline (oracle port)
-def cpu_reference_sample(S0, S, E, reps, threads=None):
+def cpu_reference_sample(S0, S, E, reps, threads=None, inner_warm=True):
     """Times the oracle (CPU fp32 restatement of the reference, pinned to its own classes) on the host cores: per stage,
     one forward + scheduler step at batch 1, `reps` timed repetitions after one warm-up; extrapolated to the
     4 x 1000-step cascade.  Returns (B-reps/s, cores, description)."""
@@ -103,14 +103,16 @@ def cpu_reference_sample(S0, S, E, reps, threads=None):
             fwd = {"surfpos": lambda: O.surfpos_forward(sd, x, t), "surfz": lambda: O.surfz_forward(sd, x, t, sP, fm),
                    "edgepos": lambda: O.edgepos_forward(sd, x, t, sP, sZ, fm),
                    "edgez": lambda: O.edgez_forward(sd, x, t, eP, sP, sZ, em)}[kind]
-            orc.step(fwd(), 500, x, r(*shape))
+            if inner_warm:
+                orc.step(fwd(), 500, x, r(*shape))
             t0 = time.perf_counter()
             for _ in range(reps):
                 orc.step(fwd(), 500, x, r(*shape))
             per[name] = (time.perf_counter() - t0) / reps
             del sd
     sec_per_brep = 750 * per["surfpos@S0"] + 250 * per["surfpos@S"] + 1000 * (per["surfz"] + per["edgepos"] + per["edgez"])
-    desc = ("oracle fp32 (torch CPU), batch 1, 1 warm + %d timed (forward + DDPM step) per stage; s/step: " % reps +
+    desc = ("oracle fp32 (torch CPU, %d threads), batch 1, %d timed (forward + DDPM step) per stage after warm-up; s/step: "
+            % (cores, reps) +
             ", ".join(f"{k}={v:.3f}" for k, v in per.items()) + "; extrapolated to 750/250 + 3x1000 steps")
     return 1.0 / sec_per_brep, cores, desc
 
@@ -176,10 +178,12 @@ def run_reference(args):
     vals = []
     nthr = best_cpu_threads()
     for _ in range(max(args.warmup, 0)):
-        cpu_reference_sample(S0, S, E, 1, nthr)
+        cpu_reference_sample(S0, S, E, 1, nthr, inner_warm=False)
+    if args.warmup == 0:
+        cpu_reference_sample(S0, S, E, 1, nthr, inner_warm=False)      # never time a cold first pass
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        v, cores, desc = cpu_reference_sample(S0, S, E, 1, nthr)
+        v, cores, desc = cpu_reference_sample(S0, S, E, 1, nthr, inner_warm=False)
         vals.append(v)
     ms = (time.perf_counter() - t0) / max(args.steps, 1) * 1e3
     v = sum(vals) / len(vals)
