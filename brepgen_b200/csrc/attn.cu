@@ -63,6 +63,8 @@ struct AttnParams {
   const int* blk_list;
   const int* blk_count;
   float scale_log2;   // log2(e) / sqrt(64)
+  int pingpong;       // XU token between the two softmax warpgroups (named barriers)
+  int probe;          // early non-blocking mbarrier probes
 };
 
 // PM: 4-bit mask over the 4 element pairs of each 8-key chunk whose exp2 runs as a polynomial on the FMA pipe instead of
@@ -219,11 +221,11 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
 
     float m_ref = -INFINITY, l = 0.f;
 
-    // Ping-pong of the two softmax warpgroups over the XU (MUFU.EX2) pipe, which is the binding unit: warpgroup t runs
-    // its exponential phase only while holding the token (named barrier 1 + t); meanwhile the other warpgroup does its
-    // TMEM load / row max / fences.  Without this both warpgroups run in lock-step and fight for the XU pipe.
-    if (NT == 2 && t == 1 && nblk > 0) named_bar_arrive(1, 256);
-
+    // mbarrier probes cost ~150 cycles of latency even when the phase has long completed; they are therefore ISSUED
+    // early (non-blocking test_wait) and only CONSUMED where the data is needed, with a blocking wait as the fallback.
+    bool s_ready = false;
+    const bool pingpong = NT == 2 && p.pingpong != 0;
+    if (pingpong && t == 1 && nblk > 0) named_bar_arrive(1, 256);
     for (int it = 0; it < nblk; ++it) {
       const uint4 iw = *reinterpret_cast<const uint4*>(maskw + it * 4);
       const uint32_t inval[4] = {iw.x, iw.y, iw.z, iw.w};
@@ -233,7 +235,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
       const bool trace = blockIdx.x == 3 && blockIdx.y == 5 && blockIdx.z == 2 && (threadIdx.x & 127) == 0 && it < 32;
       tr[0] = clock64();
 #endif
-      mbar_wait(&s_full[t], it & 1);
+      if (!s_ready) mbar_wait(&s_full[t], it & 1);
       tc_fence_after();
 #ifdef BG_ATTN_TRACE
       tr[1] = clock64();
@@ -241,6 +243,9 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
       float s[128];
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) tmem_ld_32x32b_x32(s_tmem + cc * 32, reinterpret_cast<uint32_t*>(s) + cc * 32);
+      // probe "PV of the previous block done" while the TMEM load is in flight (PB == 1: one barrier per tile)
+      bool pv_ready = it == 0;
+      if (it > 0 && p.probe) pv_ready = mbar_test_wait(&pv_full[t * C::PB + (it - 1) % C::PB], ((it - 1) / C::PB) & 1);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&s_free[t]);          // S_t may be overwritten by QK^T of the next block
@@ -268,7 +273,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
       } else {
         const bool need = (m_new - m_ref) * c > 8.f;
         if (__any_sync(0xffffffffu, need)) {
-          wait_pv(it - 1);                // O_t complete up to block it-1 before its read-modify-write
+          if (!pv_ready) wait_pv(it - 1); // O_t complete up to block it-1 before its read-modify-write
+          pv_ready = true;
           tc_fence_after();
           const float f = need ? ex2((m_ref - m_new) * c) : 1.f;
 #pragma unroll
@@ -288,11 +294,13 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
 #ifdef BG_ATTN_TRACE
       tr[3] = clock64();
 #endif
-      if (it >= C::PB) wait_pv(it - C::PB);   // the PV MMA that read this P buffer has finished
+      if (it >= C::PB && !pv_ready) wait_pv(it - C::PB);   // the PV MMA that read this P buffer has finished
+      // probe the next block's scores now; the answer is consumed at the top of the next iteration
+      s_ready = (p.probe && it + 1 < nblk) ? mbar_test_wait(&s_full[t], (it + 1) & 1) : false;
+      if (pingpong) named_bar_sync(1 + t, 256);
 #ifdef BG_ATTN_TRACE
       tr[4] = clock64();
 #endif
-      if (NT == 2) named_bar_sync(1 + t, 256);
 #ifdef BG_ATTN_TRACE
       tr[5] = clock64();
 #endif
@@ -346,7 +354,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
 #ifdef BG_ATTN_TRACE
       tr[6] = clock64();
 #endif
-      if (NT == 2 && !(t == 1 && it == nblk - 1)) named_bar_arrive(1 + (1 - t), 256);   // hand the XU token over
+      if (pingpong && !(t == 1 && it == nblk - 1)) named_bar_arrive(1 + (1 - t), 256);   // hand the XU token over
       tc_fence_before();                // orders the (rare) O rescale before the PV MMA that p_full releases
       if (PT) {
         tmem_st_32x32b_x32(s_tmem + 192, ppk);
@@ -452,6 +460,12 @@ int launch_attention(cudaStream_t st, const AttnArgs& a) {
   p.out = a.out; p.ldo = a.ldo; p.B = a.B; p.L = a.L; p.nkb = (a.L + 127) / 128;
   p.key_mask = a.key_mask; p.blk_list = a.blk_list; p.blk_count = a.blk_count;
   p.scale_log2 = 1.4426950408889634f / 8.0f;
+  {
+    const char* e1 = getenv("BG_ATTN_PP");
+    const char* e2 = getenv("BG_ATTN_PROBE");
+    p.pingpong = e1 ? atoi(e1) : 1;
+    p.probe = e2 ? atoi(e2) : 0;
+  }
   static int nt1 = -1;                  // BG_ATTN_NT1 = 1: one query tile per CTA, two CTAs per SM, for every L
   if (nt1 < 0) {
     const char* e = getenv("BG_ATTN_NT1");
