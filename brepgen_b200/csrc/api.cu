@@ -50,7 +50,9 @@ int bg_op_attention(const void* qkv, void* out, int B, int L, const uint8_t* key
     const int nkb = (L + 127) / 128;
     a.blk_list = scratch_int;
     a.blk_count = scratch_int + (size_t)B * nkb;
-    BG_TRY(launch_build_block_list(st, key_mask, B, L, scratch_int, scratch_int + (size_t)B * nkb));
+    uint32_t* words = reinterpret_cast<uint32_t*>(scratch_int + (size_t)B * (nkb + 1));
+    a.blk_words = words;
+    BG_TRY(launch_build_block_list(st, key_mask, B, L, scratch_int, scratch_int + (size_t)B * nkb, words));
   }
   return launch_attention(st, a);
 }

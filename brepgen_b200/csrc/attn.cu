@@ -62,6 +62,7 @@ struct AttnParams {
   const uint8_t* key_mask;
   const int* blk_list;
   const int* blk_count;
+  const uint32_t* blk_words;   // [B][nkb][4] invalid-key bit words per 128-key block (built once per forward), or null
   float scale_log2;   // log2(e) / sqrt(64)
   int pingpong;       // XU token between the two softmax warpgroups (named barriers)
   int probe;          // early non-blocking mbarrier probes
@@ -115,19 +116,47 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
       for (int i = 0; i < C::PB; ++i) mbar_init(&pv_full[t * C::PB + i], 1);
     }
     fence_barrier_init();
+    // start the first loads right away (this thread initialised the barriers itself): they overlap with the TMEM
+    // allocation, the mask-word construction and the CTA-wide synchronisation below
+    mbar_arrive_expect_tx(q_full, NT * TILE_BYTES);
+    for (int t = 0; t < NT; ++t)
+      tma_load_3d(smem + C::OFF_Q + t * TILE_BYTES, &tmQKV, q_full, h * DH, (qgrp * NT + t) * 128, b);
+    for (int it = 0; it < nblk && it < C::ST; ++it) {
+      const int kb = blist ? blist[it] : it;
+      mbar_arrive_expect_tx(&k_full[it], TILE_BYTES);
+      tma_load_3d(smem + C::OFF_K + it * TILE_BYTES, &tmQKV, &k_full[it], DMODEL + h * DH, kb * 128, b);
+      mbar_arrive_expect_tx(&v_full[it], TILE_BYTES);
+      tma_load_3d(smem + C::OFF_V + it * TILE_BYTES, &tmQKV, &v_full[it], 2 * DMODEL + h * DH, kb * 128, b);
+    }
   }
   if (warp == MMA_WARP) tmem_alloc<C::TMEM_COLS>(tmem_slot);
   // invalid-key bit words for every key block this CTA will visit (padded key or key >= L), built once: keeps the
   // global mask bytes off the per-block critical path
   uint32_t* maskw = reinterpret_cast<uint32_t*>(smem + C::OFF_MASKW);
   if (warp < PRODUCER_WARP) {
-    for (int wi = warp; wi < nblk * 4; wi += PRODUCER_WARP) {
-      const int kb = blist ? blist[wi >> 2] : (wi >> 2);
-      const int key = kb * 128 + (wi & 3) * 32 + lane;
-      bool bad = key >= p.L;
-      if (!bad && p.key_mask) bad = p.key_mask[(size_t)b * p.L + key] != 0;
-      const uint32_t w = __ballot_sync(0xffffffffu, bad);
-      if (lane == 0) maskw[wi] = w;
+    if (p.blk_words || !p.key_mask) {
+      // one word per thread, no dependent global-load chain: either copied from the per-forward table or, without a
+      // mask, computed (only keys >= L are invalid)
+      for (int wi = threadIdx.x; wi < nblk * 4; wi += PRODUCER_WARP * 32) {
+        const int kb = blist ? blist[wi >> 2] : (wi >> 2);
+        uint32_t w;
+        if (p.blk_words) {
+          w = p.blk_words[((size_t)b * p.nkb + kb) * 4 + (wi & 3)];
+        } else {
+          const int base = kb * 128 + (wi & 3) * 32;
+          w = base + 32 <= p.L ? 0u : (base >= p.L ? 0xffffffffu : (0xffffffffu << (p.L - base)));
+        }
+        maskw[wi] = w;
+      }
+    } else {
+      for (int wi = warp; wi < nblk * 4; wi += PRODUCER_WARP) {
+        const int kb = blist ? blist[wi >> 2] : (wi >> 2);
+        const int key = kb * 128 + (wi & 3) * 32 + lane;
+        bool bad = key >= p.L;
+        if (!bad && p.key_mask) bad = p.key_mask[(size_t)b * p.L + key] != 0;
+        const uint32_t w = __ballot_sync(0xffffffffu, bad);
+        if (lane == 0) maskw[wi] = w;
+      }
     }
   }
   tc_fence_before();
@@ -141,10 +170,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
    if constexpr (NT == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
    if (warp == PRODUCER_WARP) {
     if (elect_one()) {
-      mbar_arrive_expect_tx(q_full, NT * TILE_BYTES);
-      for (int t = 0; t < NT; ++t)
-        tma_load_3d(smem + C::OFF_Q + t * TILE_BYTES, &tmQKV, q_full, h * DH, (qgrp * NT + t) * 128, b);
-      for (int it = 0; it < nblk; ++it) {
+      for (int it = C::ST; it < nblk; ++it) {       // the first ST blocks were issued before the CTA-wide sync
         const int kb = blist ? blist[it] : it;
         const int s = it % C::ST;
         const uint32_t par = ((it / C::ST) & 1) ^ 1;
@@ -411,17 +437,20 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
 
 // one CTA per sample: which 128-key blocks hold at least one valid key
 __global__ void block_list_kernel(const uint8_t* __restrict__ key_mask, int L, int nkb, int* __restrict__ blk_list,
-                                  int* __restrict__ blk_count) {
+                                  int* __restrict__ blk_count, uint32_t* __restrict__ blk_words) {
   extern __shared__ int flags[];
   const int b = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   for (int kb = warp; kb < nkb; kb += nwarp) {
     bool any = false;
-    for (int i = lane; i < 128; i += 32) {
-      const int key = kb * 128 + i;
-      if (key < L && key_mask[(size_t)b * L + key] == 0) any = true;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int key = kb * 128 + c * 32 + lane;
+      const bool bad = key >= L || key_mask[(size_t)b * L + key] != 0;
+      const uint32_t w = __ballot_sync(0xffffffffu, bad);
+      any = any || w != 0xffffffffu;
+      if (lane == 0 && blk_words) blk_words[((size_t)b * nkb + kb) * 4 + c] = w;
     }
-    any = __any_sync(0xffffffffu, any);
     if (lane == 0) flags[kb] = any ? 1 : 0;
   }
   __syncthreads();
@@ -458,7 +487,7 @@ int launch_attention(cudaStream_t st, const AttnArgs& a) {
   BG_TRY(make_tmap_3d_f16(&tm, a.qkv, (uint64_t)a.B, (uint64_t)a.L, 3 * DMODEL, 3 * DMODEL, 128));
   AttnParams p;
   p.out = a.out; p.ldo = a.ldo; p.B = a.B; p.L = a.L; p.nkb = (a.L + 127) / 128;
-  p.key_mask = a.key_mask; p.blk_list = a.blk_list; p.blk_count = a.blk_count;
+  p.key_mask = a.key_mask; p.blk_list = a.blk_list; p.blk_count = a.blk_count; p.blk_words = a.blk_words;
   p.scale_log2 = 1.4426950408889634f / 8.0f;
   {
     const char* e1 = getenv("BG_ATTN_PP");
@@ -498,10 +527,11 @@ int launch_attention(cudaStream_t st, const AttnArgs& a) {
   return launch_nt<2, 0x8, 0>(st, tm, p);
 }
 
-int launch_build_block_list(cudaStream_t st, const uint8_t* key_mask, int B, int L, int* blk_list, int* blk_count) {
+int launch_build_block_list(cudaStream_t st, const uint8_t* key_mask, int B, int L, int* blk_list, int* blk_count,
+                            uint32_t* blk_words) {
   BG_REQUIRE(key_mask && blk_list && blk_count && B > 0 && L > 0, "block list: bad arguments");
   const int nkb = (L + 127) / 128;
-  block_list_kernel<<<B, 128, nkb * sizeof(int), st>>>(key_mask, L, nkb, blk_list, blk_count);
+  block_list_kernel<<<B, 128, nkb * sizeof(int), st>>>(key_mask, L, nkb, blk_list, blk_count, blk_words);
   return check_launch("block_list_kernel launch");
 }
 

@@ -323,6 +323,7 @@ struct Workspace {
   __half *Xn, *QKV, *AO, *Hff, *Hface;
   uint8_t* mask;
   int *blk_list, *blk_count;
+  uint32_t* blk_words;
   size_t bytes;
 };
 
@@ -348,6 +349,7 @@ Workspace carve(char* base, int kind, int B, int S, int E) {
   w.mask = reinterpret_cast<uint8_t*>(take(M));
   w.blk_list = reinterpret_cast<int*>(take((size_t)B * nkb * 4));
   w.blk_count = reinterpret_cast<int*>(take((size_t)B * 4));
+  w.blk_words = reinterpret_cast<uint32_t*>(take((size_t)B * nkb * 16));
   w.bytes = off;
   return w;
 }
@@ -467,7 +469,7 @@ int bg_denoiser_forward(BgDenoiser* m, const BgDenoiserArgs* a, void* workspace,
     } else {
       kmask = a->mask;
     }
-    BG_TRY(launch_build_block_list(st, kmask, B, L, w.blk_list, w.blk_count));
+    BG_TRY(launch_build_block_list(st, kmask, B, L, w.blk_list, w.blk_count, w.blk_words));
   }
 
   // 4. encoder
@@ -488,6 +490,7 @@ int bg_denoiser_forward(BgDenoiser* m, const BgDenoiserArgs* a, void* workspace,
       at.qkv = w.QKV; at.out = w.AO; at.ldo = D; at.B = B; at.L = L; at.key_mask = kmask;
       at.blk_list = kmask ? w.blk_list : nullptr;
       at.blk_count = kmask ? w.blk_count : nullptr;
+      at.blk_words = kmask ? w.blk_words : nullptr;
       BG_TRY(launch_attention(st, at));
     }
     {

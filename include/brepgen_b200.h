@@ -138,7 +138,7 @@ int bg_op_gemm_f16(const void* A, int lda, const void* W, int ldw, int M, int N,
                    int relu, const float* bias, const float* resid, int ldr, const float* rowvec, int rows_per_vec,
                    int ldv, void* stream);
 /* qkv fp16 [B*L][2304] -> out fp16 [B*L][768]; key_mask (B,L) or NULL; use_block_list: skip fully padded key blocks
- * (needs scratch_int of B*(ceil(L/128)+1) ints) */
+ * (needs scratch_int of B*(5*ceil(L/128)+1) ints: block list, counts and the invalid-key bit words) */
 int bg_op_attention(const void* qkv, void* out, int B, int L, const uint8_t* key_mask, int use_block_list,
                     int* scratch_int, void* stream);
 int bg_op_layernorm_f16(const float* x, int ldx, const float* gamma, const float* beta, void* y, int ldy, int rows,

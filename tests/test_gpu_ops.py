@@ -118,7 +118,7 @@ def test_attention(B, L, mkind, blist):
     ref = _attn_ref(qkv, B, L, mask)
     out = torch.full((B * L, 768), float("nan"), device="cuda", dtype=torch.float16)
     nkb = (L + 127) // 128
-    scratch = torch.zeros(B * (nkb + 1), dtype=torch.int32, device="cuda")
+    scratch = torch.zeros(B * (5 * nkb + 1), dtype=torch.int32, device="cuda")
     f.check(f.lib().bg_op_attention(qkv.data_ptr(), out.data_ptr(), B, L, f.ptr(mask), blist, scratch.data_ptr(),
                                    f.current_stream()), "attention")
     torch.cuda.synchronize()
