@@ -311,8 +311,11 @@ def main():
     L = S * E
     qkv = (torch.randn(B * L, 2304, device=dev, dtype=torch.float16))
     ao = torch.empty(B * L, 768, device=dev, dtype=torch.float16)
-    attn = lambda: _ffi.check(_ffi.lib().bg_op_attention(qkv.data_ptr(), ao.data_ptr(), B, L, None, 0, None,
-                                                          _ffi.current_stream()))
+    # same call form as inside the cascade: an (all-valid) key-padding mask plus the per-forward block list / bit words
+    amask = torch.zeros(B, L, dtype=torch.bool, device=dev)
+    ascr = torch.zeros(B * (5 * ((L + 127) // 128) + 1), dtype=torch.int32, device=dev)
+    attn = lambda: _ffi.check(_ffi.lib().bg_op_attention(qkv.data_ptr(), ao.data_ptr(), B, L, amask.data_ptr(), 1,
+                                                          ascr.data_ptr(), _ffi.current_stream()))
     for _ in range(2):
         attn()
     ms_attn = timed(attn, 5)
