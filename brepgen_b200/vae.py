@@ -23,7 +23,7 @@ from .spec import (CUBIC_DOWN_KERNEL, CUBIC_UP_KERNEL, edge_decoder_spec, edge_e
 from .synth import synth_state_dict
 
 
-class _Decoder(nn.Module):
+class _VaeModule(nn.Module):
     kind = 0
     chunk = 1024          # samples per library call (bounds the im2col workspace)
 
@@ -101,7 +101,7 @@ class _Decoder(nn.Module):
         return out
 
 
-class AutoencoderKLFastDecode(_Decoder):
+class AutoencoderKLFastDecode(_VaeModule):
     kind = 0
     chunk = 1024
 
@@ -114,7 +114,7 @@ class AutoencoderKLFastDecode(_Decoder):
         super().__init__(surf_decoder_spec(), dict(block_out_channels=[128, 256, 512, 512]), cfg)
 
 
-class AutoencoderKL1DFastDecode(_Decoder):
+class AutoencoderKL1DFastDecode(_VaeModule):
     kind = 1
     chunk = 32768
 
@@ -127,7 +127,7 @@ class AutoencoderKL1DFastDecode(_Decoder):
         super().__init__(edge_decoder_spec(), dict(block_out_channels=[128, 256, 512]), cfg)
 
 
-class AutoencoderKLFastEncode(_Decoder):
+class AutoencoderKLFastEncode(_VaeModule):
     """network.py:861-945: forward(x (N,3,H,W)) -> DiagonalGaussianDistribution(quant_conv(encoder(x))).mode()"""
     kind = 2
     chunk = 1024
@@ -141,7 +141,7 @@ class AutoencoderKLFastEncode(_Decoder):
                          dict(block_out_channels=block_out_channels))
 
 
-class AutoencoderKL1DFastEncode(_Decoder):
+class AutoencoderKL1DFastEncode(_VaeModule):
     """network.py:690-783: forward(x (N,3,32)) -> latent mode (N,3,4)"""
     kind = 3
     chunk = 32768
