@@ -73,8 +73,11 @@ struct AttnParams {
 // PT: P goes to TENSOR MEMORY (tcgen05.st, two fp16 per column) and the PV MMA takes its A operand from TMEM -- per key
 // block this removes 64 KB of shared-memory writes + 64 KB of reads, which otherwise make the kernel smem-bandwidth bound
 // (QK^T and PV operand reads + P + TMA fills = 256 KB per block ~ 2048 cycles at 128 B/clk vs 1024 MMA cycles).
-template <int NT, int PM, int PT>
-__global__ void __launch_bounds__(ACfg<NT>::THREADS, (NT == 2) ? 1 : 2)
+// HW: two extra "helper" warps (a 4th warpgroup, 512 threads) do the mbarrier waits for S-ready / PV-done ahead of time
+// and release the softmax warpgroups through named barriers: an mbarrier probe costs ~150-230 cycles of latency on the
+// softmax critical path even when the phase completed long ago, a named-barrier sync ~15.
+template <int NT, int PM, int PT, int HW>
+__global__ void __launch_bounds__(HW ? 512 : ACfg<NT>::THREADS, (NT == 2) ? 1 : 2)
 attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   using C = ACfg<NT>;
   extern __shared__ uint8_t smem_raw[];
@@ -167,7 +170,24 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   // register rebalancing (NT == 2): the softmax warpgroups hold a 128-wide score row per thread; the third warpgroup
   // (producer, MMA issuer, two idle warps) gives its registers away.  Each role sets its budget inside its own branch.
   if (warp >= PRODUCER_WARP) {
-   if constexpr (NT == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+   if constexpr (NT == 2 && HW) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+   else if constexpr (NT == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+   if (HW && warp >= 12 && warp < 12 + NT) {
+    // helper warp of tile t: named barrier 3 + t = "S_t of this block is in TMEM", 5 + t = "PV_t of the previous block done"
+    const int t = warp - 12;
+    for (int it = 0; it < nblk; ++it) {
+      mbar_wait(&s_full[t], it & 1);
+      named_bar_arrive(3 + t, 160);
+      if (it > 0) {
+        mbar_wait(&pv_full[t * C::PB], (it - 1) & 1);
+        named_bar_arrive(5 + t, 160);
+      }
+    }
+    if (nblk > 0) {
+      mbar_wait(&pv_full[t * C::PB], (nblk - 1) & 1);
+      named_bar_arrive(5 + t, 160);
+    }
+   } else
    if (warp == PRODUCER_WARP) {
     if (elect_one()) {
       for (int it = C::ST; it < nblk; ++it) {       // the first ST blocks were issued before the CTA-wide sync
@@ -229,7 +249,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
     }
    }
   } else {
-    if constexpr (NT == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    if constexpr (NT == 2 && HW) asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    else if constexpr (NT == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     // ------------------------------------------------------------------ softmax warpgroup for query tile t
     // One thread per query row (== TMEM lane).  The whole 128-key score row lives in registers (one TMEM read, S is
     // released to the next QK^T right away); O accumulates in TMEM across key blocks and is rescaled lazily: the
@@ -242,7 +263,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
     const uint32_t o_tmem = s_tmem + 128;
     const uint32_t sP0 = smem_u32(smem + C::OFF_P + t * C::PB * P_BYTES) + r * 128;
     // PV(i) reads P buffer i % PB and completes on pv_full[t][i % PB] (its (i / PB)-th completion)
-    auto wait_pv = [&](int i) { mbar_wait(&pv_full[t * C::PB + i % C::PB], (i / C::PB) & 1); };
+    auto wait_pv = [&](int i) {
+      if (HW) named_bar_sync(5 + t, 160);
+      else mbar_wait(&pv_full[t * C::PB + i % C::PB], (i / C::PB) & 1);
+    };
     const float c = p.scale_log2;
 
     float m_ref = -INFINITY, l = 0.f;
@@ -261,7 +285,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
       const bool trace = blockIdx.x == 3 && blockIdx.y == 5 && blockIdx.z == 2 && (threadIdx.x & 127) == 0 && it < 32;
       tr[0] = clock64();
 #endif
-      if (!s_ready) mbar_wait(&s_full[t], it & 1);
+      if (HW) named_bar_sync(3 + t, 160);
+      else if (!s_ready) mbar_wait(&s_full[t], it & 1);
       tc_fence_after();
 #ifdef BG_ATTN_TRACE
       tr[1] = clock64();
@@ -271,7 +296,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
       for (int cc = 0; cc < 4; ++cc) tmem_ld_32x32b_x32(s_tmem + cc * 32, reinterpret_cast<uint32_t*>(s) + cc * 32);
       // probe "PV of the previous block done" while the TMEM load is in flight (PB == 1: one barrier per tile)
       bool pv_ready = it == 0;
-      if (it > 0 && p.probe) pv_ready = mbar_test_wait(&pv_full[t * C::PB + (it - 1) % C::PB], ((it - 1) / C::PB) & 1);
+      if (!HW && it > 0 && p.probe) pv_ready = mbar_test_wait(&pv_full[t * C::PB + (it - 1) % C::PB], ((it - 1) / C::PB) & 1);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&s_free[t]);          // S_t may be overwritten by QK^T of the next block
@@ -322,7 +347,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
 #endif
       if (it >= C::PB && !pv_ready) wait_pv(it - C::PB);   // the PV MMA that read this P buffer has finished
       // probe the next block's scores now; the answer is consumed at the top of the next iteration
-      s_ready = (p.probe && it + 1 < nblk) ? mbar_test_wait(&s_full[t], (it + 1) & 1) : false;
+      s_ready = (!HW && p.probe && it + 1 < nblk) ? mbar_test_wait(&s_full[t], (it + 1) & 1) : false;
       if (pingpong) named_bar_sync(1 + t, 256);
 #ifdef BG_ATTN_TRACE
       tr[4] = clock64();
@@ -462,17 +487,17 @@ __global__ void block_list_kernel(const uint8_t* __restrict__ key_mask, int L, i
   }
 }
 
-template <int NT, int PM, int PT>
+template <int NT, int PM, int PT, int HW = 0>
 int launch_nt(cudaStream_t st, const CUtensorMap& tm, const AttnParams& p) {
   using C = ACfg<NT>;
   static bool configured = false;
   if (!configured) {
-    BG_CUDA(cudaFuncSetAttribute(attn_kernel<NT, PM, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    BG_CUDA(cudaFuncSetAttribute(attn_kernel<NT, PM, PT, HW>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     configured = true;
   }
   const int nq = (p.L + 127) / 128;
   dim3 grid((nq + NT - 1) / NT, NHEAD, p.B);
-  attn_kernel<NT, PM, PT><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(tm, p);
+  attn_kernel<NT, PM, PT, HW><<<grid, HW ? 512 : C::THREADS, C::SMEM_BYTES, st>>>(tm, p);
   return check_launch("attn_kernel launch");
 }
 
@@ -522,6 +547,12 @@ int launch_attention(cudaStream_t st, const AttnArgs& a) {
     if (poly == 2) return launch_nt<2, 0xA, 1>(st, tm, p);
     return launch_nt<2, 0x8, 1>(st, tm, p);
   }
+  static int helper = -1;               // helper warps turn mbarrier waits into named-barrier syncs (BG_ATTN_HELPER=0: off)
+  if (helper < 0) {
+    const char* e = getenv("BG_ATTN_HELPER");
+    helper = e ? atoi(e) : 1;
+  }
+  if (helper) return poly == 0 ? launch_nt<2, 0x0, 0, 1>(st, tm, p) : launch_nt<2, 0x8, 0, 1>(st, tm, p);
   if (poly == 0) return launch_nt<2, 0x0, 0>(st, tm, p);
   if (poly == 2) return launch_nt<2, 0xA, 0>(st, tm, p);
   return launch_nt<2, 0x8, 0>(st, tm, p);
