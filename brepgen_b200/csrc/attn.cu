@@ -6,9 +6,11 @@
 // online-softmax (flash) kernel; the surface stages (L <= 100) use the same kernel with one key block.
 //
 // CTA = NT query tiles of 128 rows for one (sample, head):
-//   warps [0, 4*NT) : softmax warpgroups, one per query tile; thread r owns query row r == TMEM lane r
-//   warp 4*NT       : TMA producer (Q once; K / V 128-key tiles through an ST-deep mbarrier ring)
-//   warp 4*NT+1     : TMEM allocator + MMA issuer (one elected thread)
+//   warps [0, 4*NT)   : softmax warpgroups, one per query tile; thread r owns query row r == TMEM lane r
+//   warp 4*NT         : TMA producer (Q once; K / V 128-key tiles through an ST-deep mbarrier ring)
+//   warps 4*NT+1 ..   : one MMA-issuing thread per query tile (the first of these warps owns the TMEM allocation)
+//   warps 12, 13 (HW) : helper warps: wait on the S-ready / PV-done mbarriers ahead of time and release the softmax
+//                       warpgroup of their tile through named barriers
 // per key block j and tile t:   S_t = Q_t K_j^T            4 x tcgen05.mma M128 N128 K16  (A,B K-major SW128)
 //                               P_t = exp2(c (S_t - m))     softmax WG: TMEM -> regs -> fp16 -> swizzled smem
 //                               O_t (+)= P_t V_j            8 x tcgen05.mma M128 N64 K16   (B = V, MN-major SW128)
