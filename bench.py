@@ -44,6 +44,9 @@ def parse():
     ap.add_argument("--surfaces", type=int, default=50)
     ap.add_argument("--edges", type=int, default=40)
     ap.add_argument("--steps-per-stage", type=int, default=4)
+    ap.add_argument("--cf", action="store_true", help="classifier-free guidance (furniture config: 2x forward batch, no late increase)")
+    ap.add_argument("--schedule", default="ddpm", choices=["ddpm", "reference"],
+                    help="ddpm = N DDPM steps per stage (the metric's definition); reference = the shipped PNDM/DDPM hybrid")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -223,11 +226,11 @@ def main():
     _ffi.check(_ffi.lib().bg_check_device(), "bg_check_device")
 
     B, S0, E, T = args.batch, args.surfaces, args.edges, args.steps_per_stage
-    S = 2 * S0
+    S = S0 if args.cf else 2 * S0
     models = {}
     for kind in KINDS:
-        m = NETS[kind](False)
-        m.load_state_dict(synth_state_dict(denoiser_spec(kind, False), seed=1))
+        m = NETS[kind](args.cf)
+        m.load_state_dict(synth_state_dict(denoiser_spec(kind, args.cf), seed=1))
         models[kind] = m.to(dev).eval()
     surf_vae = edge_vae = None
     try:
@@ -236,8 +239,8 @@ def main():
     except ImportError:
         pass
     casc = Cascade(models, surf_vae, edge_vae, device=dev)
-    cfg = CascadeConfig(batch_size=B, num_surfaces=S0, num_edges=E, schedule="ddpm", ddpm_steps=T, dense_masks=True,
-                        seed=1000 + rank, decode=surf_vae is not None)
+    cfg = CascadeConfig(batch_size=B, num_surfaces=S0, num_edges=E, use_cf=args.cf, class_label=6, schedule=args.schedule,
+                        ddpm_steps=T, dense_masks=True, seed=1000 + rank, decode=surf_vae is not None)
     g = torch.Generator().manual_seed(1000 + rank)
     shapes = {"surfPos": (B, S0, 6), "surfZ": (B, S, 48), "edgePos": (B, S, E, 6), "edgeZV": (B, S, E, 18)}
     host_in = {k: torch.randn(s, generator=g).pin_memory() for k, s in shapes.items()}
@@ -273,7 +276,7 @@ def main():
     ms = timed(step_resident, args.steps)
     launches = _ffi.lib().bg_launch_count() - l0
     clk = clocks.finish()
-    scale = 1000.0 / T
+    scale = 1000.0 / T if args.schedule == "ddpm" else 1.0     # the shipped hybrid is run literally
     # the two VAE decodes run once per cascade whatever T is: time them alone and keep them out of the 1000/T scaling
     ms_dec = 0.0
     if surf_vae is not None:
@@ -331,7 +334,8 @@ def main():
     roofline = {"bound": "tensor", "kernel": "attn_kernel<2> (tcgen05 flash attention, B=%d L=%d)" % (B, L),
                 "achieved": ach, "peak": burst, "unit": "TFLOP/s", "frac": ach / burst, "peak_source": f"bf16_tflops burst, {src}",
                 "traffic": traffic, "ms_per_launch": ms_attn, "flop_per_launch": fl_attn}
-    flops_brep = cascade_flops_per_brep(S0, S, E)
+    # CFG doubles every forward; the shipped hybrid runs 158 PNDM + 250 DDPM forwards per stage (sample.py:128-155)
+    flops_brep = cascade_flops_per_brep(S0, S, E, steps=1000 if args.schedule == "ddpm" else 408) * (2 if args.cf else 1)
     whole = {"algorithmic_tflop_per_brep": flops_brep / 1e12, "achieved_tflops_per_gpu": value / world * flops_brep / 1e12,
              "frac_of_sustained_peak": value / world * flops_brep / 1e12 / sustained}
 
@@ -345,7 +349,8 @@ def main():
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f16 x f16 -> f32 (tcgen05 kind::f16; split hi+lo weights on in/out-proj; fp32 residual/LN/softmax)",
                 "data": "synthetic",
-                "config": {"workload": f"abc_cascade B={B}/GPU S0={S0}->S={S} E={E} L_edge={L}, dense masks",
+                "config": {"workload": f"{'furniture_cfg' if args.cf else 'abc'}_cascade B={B}/GPU S0={S0}->S={S} E={E} L_edge={L}, "
+                                       f"dense masks, schedule={args.schedule}",
                            "ddpm_steps_per_stage_timed": T, "value_normalised_to_steps_per_stage": 1000,
                            "vae_decode_in_step": surf_vae is not None, "vae_decode_ms_per_step": ms_dec,
                            "l2": "activations of one step (GBs) exceed the 126 MB L2; no explicit flush",
