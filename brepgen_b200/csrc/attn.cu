@@ -64,7 +64,7 @@ struct AttnParams {
   const uint8_t* key_mask;
   const int* blk_list;
   const int* blk_count;
-  const uint32_t* blk_words;   // [B][nkb][4] invalid-key bit words per 128-key block (built once per forward), or null
+  const uint32_t* blk_words;   // [B][nkb][4] invalid-key bit words of the listed blocks, list order (per forward), or null
   float scale_log2;   // log2(e) / sqrt(64)
   int pingpong;       // XU token between the two softmax warpgroups (named barriers)
   int probe;          // early non-blocking mbarrier probes
@@ -143,12 +143,11 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
       // one word per thread, no dependent global-load chain: either copied from the per-forward table or, without a
       // mask, computed (only keys >= L are invalid)
       for (int wi = threadIdx.x; wi < nblk * 4; wi += PRODUCER_WARP * 32) {
-        const int kb = blist ? blist[wi >> 2] : (wi >> 2);
         uint32_t w;
-        if (p.blk_words) {
-          w = p.blk_words[((size_t)b * p.nkb + kb) * 4 + (wi & 3)];
+        if (p.blk_words) {      // list order: entry wi >> 2 belongs to key block blist[wi >> 2]
+          w = p.blk_words[((size_t)b * p.nkb + (wi >> 2)) * 4 + (wi & 3)];
         } else {
-          const int base = kb * 128 + (wi & 3) * 32;
+          const int base = (wi >> 2) * 128 + (wi & 3) * 32;
           w = base + 32 <= p.L ? 0u : (base >= p.L ? 0xffffffffu : (0xffffffffu << (p.L - base)));
         }
         maskw[wi] = w;
@@ -462,10 +461,14 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   if (warp == MMA_WARP) tmem_dealloc<C::TMEM_COLS>(tmem_base);
 }
 
-// one CTA per sample: which 128-key blocks hold at least one valid key
+// one CTA per sample: which 128-key blocks hold at least one valid key (blk_list / blk_count), and the invalid-key bit
+// words of the LISTED blocks in list order (blk_words[b][i][4] belongs to key block blk_list[b][i]), so that the
+// attention kernels index them with their loop counter and need no dependent load
 __global__ void block_list_kernel(const uint8_t* __restrict__ key_mask, int L, int nkb, int* __restrict__ blk_list,
                                   int* __restrict__ blk_count, uint32_t* __restrict__ blk_words) {
-  extern __shared__ int flags[];
+  extern __shared__ int sm_bl[];
+  int* pos = sm_bl;                                           // list position of key block kb, or -1
+  uint32_t* wds = reinterpret_cast<uint32_t*>(sm_bl + nkb);   // [nkb][4]
   const int b = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   for (int kb = warp; kb < nkb; kb += nwarp) {
@@ -476,17 +479,24 @@ __global__ void block_list_kernel(const uint8_t* __restrict__ key_mask, int L, i
       const bool bad = key >= L || key_mask[(size_t)b * L + key] != 0;
       const uint32_t w = __ballot_sync(0xffffffffu, bad);
       any = any || w != 0xffffffffu;
-      if (lane == 0 && blk_words) blk_words[((size_t)b * nkb + kb) * 4 + c] = w;
+      if (lane == 0) wds[kb * 4 + c] = w;
     }
-    if (lane == 0) flags[kb] = any ? 1 : 0;
+    if (lane == 0) pos[kb] = any ? 0 : -1;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     int n = 0;
     for (int kb = 0; kb < nkb; ++kb)
-      if (flags[kb]) blk_list[(size_t)b * nkb + n++] = kb;
+      if (pos[kb] == 0) {
+        blk_list[(size_t)b * nkb + n] = kb;
+        pos[kb] = n++;
+      }
     blk_count[b] = n;
   }
+  __syncthreads();
+  if (blk_words)
+    for (int i = threadIdx.x; i < nkb * 4; i += blockDim.x)
+      if (pos[i >> 2] >= 0) blk_words[((size_t)b * nkb + pos[i >> 2]) * 4 + (i & 3)] = wds[i];
 }
 
 template <int NT, int PM, int PT, int HW = 0>
@@ -539,6 +549,12 @@ int launch_attention(cudaStream_t st, const AttnArgs& a) {
     rowsplit = e ? atoi(e) : 0;
   }
   if (rowsplit) return launch_attention_rowsplit(st, a, poly);
+  static int persist = -1;              // BG_ATTN_PS = 1: persistent kernel (attn_ps.cu), one CTA per SM over all work items
+  if (persist < 0) {
+    const char* e = getenv("BG_ATTN_PS");
+    persist = e ? atoi(e) : 0;
+  }
+  if (persist && poly != 2 && attention_persistent_supported(a)) return launch_attention_persistent(st, a, poly);
   static int ptmem = -1;                // BG_ATTN_PT = 1: P in tensor memory (A operand of the PV MMA from TMEM)
   if (ptmem < 0) {
     const char* e = getenv("BG_ATTN_PT");
@@ -564,7 +580,7 @@ int launch_build_block_list(cudaStream_t st, const uint8_t* key_mask, int B, int
                             uint32_t* blk_words) {
   BG_REQUIRE(key_mask && blk_list && blk_count && B > 0 && L > 0, "block list: bad arguments");
   const int nkb = (L + 127) / 128;
-  block_list_kernel<<<B, 128, nkb * sizeof(int), st>>>(key_mask, L, nkb, blk_list, blk_count, blk_words);
+  block_list_kernel<<<B, 128, nkb * 5 * sizeof(int), st>>>(key_mask, L, nkb, blk_list, blk_count, blk_words);
   return check_launch("block_list_kernel launch");
 }
 

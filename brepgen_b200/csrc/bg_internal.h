@@ -74,10 +74,12 @@ struct AttnArgs {
   const uint8_t* key_mask = nullptr;   // [B, L] nonzero = padded key (ignored), or null
   const int* blk_list = nullptr;       // [B, nkb] key blocks (of 128) with >=1 valid key, or null = all
   const int* blk_count = nullptr;      // [B]
-  const uint32_t* blk_words = nullptr; // [B, nkb, 4] invalid-key bit words (from launch_build_block_list), or null
+  const uint32_t* blk_words = nullptr; // [B, nkb, 4] invalid-key bit words in LIST order (launch_build_block_list), or null
 };
 int launch_attention(cudaStream_t st, const AttnArgs& a);
 int launch_attention_rowsplit(cudaStream_t st, const AttnArgs& a, int poly);   // attn_rs.cu, L > 128 only
+bool attention_persistent_supported(const AttnArgs& a);                       // attn_ps.cu
+int launch_attention_persistent(cudaStream_t st, const AttnArgs& a, int poly);
 // builds blk_list/blk_count from key_mask ([B,L]); nkb = ceil(L/128)
 int launch_build_block_list(cudaStream_t st, const uint8_t* key_mask, int B, int L, int* blk_list, int* blk_count,
                             uint32_t* blk_words = nullptr);

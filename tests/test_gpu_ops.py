@@ -95,6 +95,9 @@ ATTN_CASES = [
     (2, 30, None, 0), (2, 100, "tail", 0), (1, 128, None, 0), (3, 100, "rand", 1),
     (1, 300, None, 0), (2, 257, "rand", 0), (2, 1000, "blocks", 1), (2, 1000, "blocks", 0),
     (1, 4000, None, 0), (2, 1800, "tail", 1),
+    # more work items than SMs and a different number of listed key blocks per sample (persistent kernel: items of
+    # unequal length, barrier phases running across items)
+    (8, 1000, "ragged", 1), (5, 700, None, 0), (16, 300, "ragged", 1),
 ]
 
 
@@ -109,6 +112,12 @@ def test_attention(B, L, mkind, blist):
         mask[0, L // 2:] = True
     elif mkind == "rand":
         mask = torch.rand(B, L, generator=g, device="cuda") < 0.3
+        mask[:, 0] = False
+    elif mkind == "ragged":
+        nvalid = torch.randint(1, L + 1, (B,), generator=g, device="cuda")
+        nvalid[0] = L
+        mask = torch.arange(L, device="cuda")[None, :] >= nvalid[:, None]
+        mask |= torch.rand(B, L, generator=g, device="cuda") < 0.1
         mask[:, 0] = False
     elif mkind == "blocks":
         mask = torch.zeros(B, L, dtype=torch.bool, device="cuda")

@@ -16,4 +16,4 @@ e0.record()
 for _ in range(10): run()
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 10
-print(f"{os.path.basename(_ffi.LIB_PATH)} attention B={B} L={L}: {ms:.3f} ms  {B*3072*L*L/ms/1e9:.0f} TF/s")
+print(f"{os.path.basename(_ffi.LIB_PATH)} PS={os.environ.get('BG_ATTN_PS', '0')} attention B={B} L={L}: {ms:.3f} ms  {B*3072*L*L/ms/1e9:.0f} TF/s")
