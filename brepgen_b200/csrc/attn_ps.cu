@@ -57,7 +57,7 @@ struct PsParams {
   int pingpong;
 };
 
-template <int PM>
+template <int PM, int SP>
 __global__ void __launch_bounds__(THREADS, 1) attn_ps_kernel(const __grid_constant__ CUtensorMap tmQKV, const PsParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -292,23 +292,23 @@ __global__ void __launch_bounds__(THREADS, 1) attn_ps_kernel(const __grid_consta
           for (int i = 0; i < 128; ++i)
             if ((inval[i >> 5] >> (i & 31)) & 1u) s[i] = -INFINITY;
         }
-        float mx[8];
+        auto row_max = [&]() -> float {
+          float mx[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) mx[j] = fmaxf(s[2 * j], s[2 * j + 1]);
+          for (int j = 0; j < 8; ++j) mx[j] = fmaxf(s[2 * j], s[2 * j + 1]);
 #pragma unroll
-        for (int i = 16; i < 128; i += 16) {     // eight independent FMNMX3 chains
+          for (int i = 16; i < 128; i += 16) {     // eight independent FMNMX3 chains
 #pragma unroll
-          for (int j = 0; j < 8; ++j) mx[j] = fmax3(mx[j], s[i + 2 * j], s[i + 2 * j + 1]);
-        }
-        const float m_new = fmaxf(fmax3(m_ref, fmax3(mx[0], mx[1], mx[2]), fmax3(mx[3], mx[4], mx[5])), fmaxf(mx[6], mx[7]));
-
+            for (int j = 0; j < 8; ++j) mx[j] = fmax3(mx[j], s[i + 2 * j], s[i + 2 * j + 1]);
+          }
+          return fmaxf(fmax3(m_ref, fmax3(mx[0], mx[1], mx[2]), fmax3(mx[3], mx[4], mx[5])), fmaxf(mx[6], mx[7]));
+        };
         bool pv_ready = it == 0;          // it == 0: the previous item's last PV was awaited before its O read-out
-        if (it == 0) {
-          m_ref = (m_new == -INFINITY) ? 0.f : m_new;
-        } else {
+        // lazy rescale: the exponent reference only moves when the running max grew by more than 2^8
+        auto rescale_to = [&](float m_new) {
           const bool need = (m_new - m_ref) * c > 8.f;
           if (__any_sync(0xffffffffu, need)) {
-            named_bar_sync(5 + t, 160);   // O_t complete up to block it-1 before its read-modify-write
+            if (!pv_ready) named_bar_sync(5 + t, 160);   // O_t complete up to block it-1 before its read-modify-write
             pv_ready = true;
             tc_fence_after();
             const float f = need ? ex2((m_ref - m_new) * c) : 1.f;
@@ -325,53 +325,78 @@ __global__ void __launch_bounds__(THREADS, 1) attn_ps_kernel(const __grid_consta
             l *= f;
             if (need) m_ref = m_new;
           }
+        };
+        // SP ("speculative reference"): after the first block the row max is NOT computed.  The exponentials are taken
+        // against the current m_ref; if any row's block sum reaches 2^15 (so a single p could approach the fp16 range)
+        // the warp computes the true max, rescales and redoes the block.  This takes the 100-instruction FMNMX chain
+        // (~340 cycles of dependent latency) off the per-block critical path; results differ from the eager form only
+        // in which power of two P is scaled by.
+        if (it == 0) {
+          const float m_new = row_max();
+          m_ref = (m_new == -INFINITY) ? 0.f : m_new;
+        } else if (!SP) {
+          rescale_to(row_max());
         }
         if (!pv_ready) named_bar_sync(5 + t, 160);          // the PV MMA that read the P buffer has finished
+        pv_ready = true;
         if (pingpong) named_bar_sync(1 + t, 256);
 
-        const float2 c2 = make_float2(c, c);
-        const float2 nmc2 = make_float2(-m_ref * c, -m_ref * c);
-        // p = exp2(c s - c m_ref), row sum (packed f32x2 math), fp16 P into the K-major SW128 layout; software-pipelined
-        // by one 16-key group so that the MUFU.EX2 of group g are in flight while group g-1 is summed, packed and stored
-        float2 acc = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
-        float2 ecur[8], eprev[8];
-        auto exp_group = [&](int g, float2 (&e)[8]) {
+        float bsum = 0.f;
+#pragma unroll 1
+        for (int attempt = 0;; ++attempt) {
+          const float2 c2 = make_float2(c, c);
+          const float2 nmc2 = make_float2(-m_ref * c, -m_ref * c);
+          // p = exp2(c s - c m_ref), row sum (packed f32x2 math), fp16 P into the K-major SW128 layout; software-pipelined
+          // by one 16-key group so that the MUFU.EX2 of group g are in flight while group g-1 is summed, packed and stored
+          float2 acc = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+          float2 ecur[8], eprev[8];
+          auto exp_group = [&](int g, float2 (&e)[8]) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float2 a = ffma2(make_float2(s[16 * g + 2 * q], s[16 * g + 2 * q + 1]), c2, nmc2);
-            e[q] = ((PM >> (q & 3)) & 1) ? exp2_poly2(a) : make_float2(ex2(a.x), ex2(a.y));
-          }
-        };
-        auto drain_group = [&](int g, const float2 (&e)[8]) {
-#pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            uint32_t pk[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float2 v = e[4 * hh + q];
-              if (q & 1) acc1 = fadd2(acc1, v); else acc = fadd2(acc, v);
-              __half2 hv = __floats2half2_rn(v.x, v.y);
-              pk[q] = *reinterpret_cast<uint32_t*>(&hv);
+            for (int q = 0; q < 8; ++q) {
+              float2 a = ffma2(make_float2(s[16 * g + 2 * q], s[16 * g + 2 * q + 1]), c2, nmc2);
+              if ((PM >> (q & 3)) & 1) {
+                if (SP) { a.x = fminf(a.x, 126.f); a.y = fminf(a.y, 126.f); }   // keep the exponent add of the polynomial in range
+                e[q] = exp2_poly2(a);
+              } else {
+                e[q] = make_float2(ex2(a.x), ex2(a.y));
+              }
             }
-            const int j8 = 2 * g + hh;                         // 16-byte chunk (8 keys) index along the 128 keys
-            st_shared_v4(sP + (j8 >> 3) * (P_BYTES / 2) + (((j8 & 7) ^ (r & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+          };
+          auto drain_group = [&](int g, const float2 (&e)[8]) {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float2 v = e[4 * hh + q];
+                if (q & 1) acc1 = fadd2(acc1, v); else acc = fadd2(acc, v);
+                __half2 hv = __floats2half2_rn(v.x, v.y);
+                pk[q] = *reinterpret_cast<uint32_t*>(&hv);
+              }
+              const int j8 = 2 * g + hh;                         // 16-byte chunk (8 keys) index along the 128 keys
+              st_shared_v4(sP + (j8 >> 3) * (P_BYTES / 2) + (((j8 & 7) ^ (r & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+            }
+          };
+          exp_group(0, eprev);
+#pragma unroll
+          for (int g = 1; g < 8; ++g) {
+            exp_group(g, ecur);
+            drain_group(g - 1, eprev);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) eprev[q] = ecur[q];
           }
-        };
-        exp_group(0, eprev);
-#pragma unroll
-        for (int g = 1; g < 8; ++g) {
-          exp_group(g, ecur);
-          drain_group(g - 1, eprev);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) eprev[q] = ecur[q];
+          drain_group(7, eprev);
+          bsum = (acc.x + acc.y) + (acc1.x + acc1.y);
+          if (!SP || it == 0 || attempt == 1) break;
+          if (!__any_sync(0xffffffffu, !(bsum < 32768.f))) break;
+          rescale_to(row_max());          // rare: a score outgrew the reference by 2^15 / 128 or more
         }
-        drain_group(7, eprev);
         // hand the XU token over; the very last block of this CTA (tile 1, no next item) has nobody to hand it to
         if (pingpong && !(t == 1 && it == nblk - 1 && w_next >= p.total)) named_bar_arrive(1 + (1 - t), 256);
         tc_fence_before();                // orders the O rescale / the previous item's O read-out before the PV MMA
         fence_proxy_async_smem();         // generic-proxy writes of P -> visible to the tensor core (async proxy)
         mbar_arrive(&p_full[t]);
-        l += (acc.x + acc.y) + (acc1.x + acc1.y);
+        l += bsum;
       }
 
       // read-out of O_t; the next item's first QK^T and its loads are already in flight
@@ -409,14 +434,14 @@ __global__ void __launch_bounds__(THREADS, 1) attn_ps_kernel(const __grid_consta
   if (warp == MMA_WARP) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
-template <int PM>
+template <int PM, int SP>
 int launch_ps(cudaStream_t st, const CUtensorMap& tm, const PsParams& p, int ctas) {
   static bool configured = false;
   if (!configured) {
-    BG_CUDA(cudaFuncSetAttribute(attn_ps_kernel<PM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    BG_CUDA(cudaFuncSetAttribute(attn_ps_kernel<PM, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured = true;
   }
-  attn_ps_kernel<PM><<<ctas, THREADS, SMEM_BYTES, st>>>(tm, p);
+  attn_ps_kernel<PM, SP><<<ctas, THREADS, SMEM_BYTES, st>>>(tm, p);
   return check_launch("attn_ps_kernel launch");
 }
 
@@ -451,7 +476,13 @@ int launch_attention_persistent(cudaStream_t st, const AttnArgs& a, int poly) {
   const char* e1 = getenv("BG_ATTN_PP");
   p.pingpong = e1 ? atoi(e1) : 1;
   const int ctas = p.total < sms ? p.total : sms;
-  return poly == 0 ? launch_ps<0x0>(st, tm, p, ctas) : launch_ps<0x8>(st, tm, p, ctas);
+  static int spec = -1;                 // BG_ATTN_SPEC = 1: no row max after the first block (see SP in the kernel)
+  if (spec < 0) {
+    const char* e = getenv("BG_ATTN_SPEC");
+    spec = e ? atoi(e) : 0;
+  }
+  if (spec) return poly == 0 ? launch_ps<0x0, 1>(st, tm, p, ctas) : launch_ps<0x8, 1>(st, tm, p, ctas);
+  return poly == 0 ? launch_ps<0x0, 0>(st, tm, p, ctas) : launch_ps<0x8, 0>(st, tm, p, ctas);
 }
 
 }  // namespace bg
