@@ -341,13 +341,12 @@ __global__ void __launch_bounds__(THREADS, 1) attn_ps_kernel(const __grid_consta
         pv_ready = true;
         if (pingpong) named_bar_sync(1 + t, 256);
 
-        float bsum = 0.f;
-#pragma unroll 1
-        for (int attempt = 0;; ++attempt) {
+        // one pass over the 128 scores of the row: p = exp2(c s - c m_ref), row sum (packed f32x2 math), fp16 P into the
+        // K-major SW128 layout; software-pipelined by one 16-key group so that the MUFU.EX2 of group g are in flight while
+        // group g-1 is summed, packed and stored.  Returns the block's row sum.
+        auto exp_pass = [&]() -> float {
           const float2 c2 = make_float2(c, c);
           const float2 nmc2 = make_float2(-m_ref * c, -m_ref * c);
-          // p = exp2(c s - c m_ref), row sum (packed f32x2 math), fp16 P into the K-major SW128 layout; software-pipelined
-          // by one 16-key group so that the MUFU.EX2 of group g are in flight while group g-1 is summed, packed and stored
           float2 acc = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
           float2 ecur[8], eprev[8];
           auto exp_group = [&](int g, float2 (&e)[8]) {
@@ -386,10 +385,16 @@ __global__ void __launch_bounds__(THREADS, 1) attn_ps_kernel(const __grid_consta
             for (int q = 0; q < 8; ++q) eprev[q] = ecur[q];
           }
           drain_group(7, eprev);
-          bsum = (acc.x + acc.y) + (acc1.x + acc1.y);
-          if (!SP || it == 0 || attempt == 1) break;
-          if (!__any_sync(0xffffffffu, !(bsum < 32768.f))) break;
-          rescale_to(row_max());          // rare: a score outgrew the reference by 2^15 / 128 or more
+          return (acc.x + acc.y) + (acc1.x + acc1.y);
+        };
+        // SP: first pass against the current reference; the (rare) redo with the true max is a second, cold copy.
+        // ptxas does not hoist this pass above the token barrier the way it hoists the eager form's (there it fills the
+        // latency gaps of the FMNMX chain with FFMA2 / MUFU work), so with ping-pong on the two warpgroups' exponential
+        // phases are strictly serial -- see profiles/README.md v8s.
+        float bsum = exp_pass();
+        if (SP && it > 0 && __any_sync(0xffffffffu, !(bsum < 32768.f))) {
+          rescale_to(row_max());          // a score outgrew the reference by 2^15 / 128 or more
+          bsum = exp_pass();
         }
         // hand the XU token over; the very last block of this CTA (tile 1, no next item) has nobody to hand it to
         if (pingpong && !(t == 1 && it == nblk - 1 && w_next >= p.total)) named_bar_arrive(1 + (1 - t), 256);
