@@ -47,6 +47,9 @@ def parse():
     ap.add_argument("--cf", action="store_true", help="classifier-free guidance (furniture config: 2x forward batch, no late increase)")
     ap.add_argument("--schedule", default="ddpm", choices=["ddpm", "reference"],
                     help="ddpm = N DDPM steps per stage (the metric's definition); reference = the shipped PNDM/DDPM hybrid")
+    ap.add_argument("--masks", default="dense", choices=["dense", "flow"],
+                    help="dense = every slot valid, the metric's dense-FLOP mode; flow = run both dedups (sample.py:159-183,242-261) "
+                         "and mask what they remove (fully padded key blocks are then skipped)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -240,7 +243,7 @@ def main():
         pass
     casc = Cascade(models, surf_vae, edge_vae, device=dev)
     cfg = CascadeConfig(batch_size=B, num_surfaces=S0, num_edges=E, use_cf=args.cf, class_label=6, schedule=args.schedule,
-                        ddpm_steps=T, dense_masks=True, seed=1000 + rank, decode=surf_vae is not None)
+                        ddpm_steps=T, dense_masks=args.masks == "dense", seed=1000 + rank, decode=surf_vae is not None)
     g = torch.Generator().manual_seed(1000 + rank)
     shapes = {"surfPos": (B, S0, 6), "surfZ": (B, S, 48), "edgePos": (B, S, E, 6), "edgeZV": (B, S, E, 18)}
     host_in = {k: torch.randn(s, generator=g).pin_memory() for k, s in shapes.items()}
@@ -350,7 +353,7 @@ def main():
                 "dtype": "f16 x f16 -> f32 (tcgen05 kind::f16; split hi+lo weights on in/out-proj; fp32 residual/LN/softmax)",
                 "data": "synthetic",
                 "config": {"workload": f"{'furniture_cfg' if args.cf else 'abc'}_cascade B={B}/GPU S0={S0}->S={S} E={E} L_edge={L}, "
-                                       f"dense masks, schedule={args.schedule}",
+                                       f"{args.masks} masks, schedule={args.schedule}",
                            "ddpm_steps_per_stage_timed": T, "value_normalised_to_steps_per_stage": 1000,
                            "vae_decode_in_step": surf_vae is not None, "vae_decode_ms_per_step": ms_dec,
                            "l2": "activations of one step (GBs) exceed the 126 MB L2; no explicit flush",
