@@ -55,9 +55,10 @@ struct PsParams {
   const uint32_t* blk_words;   // [B][nkb][4] in list order, or null (no mask: only keys >= L are invalid)
   float scale_log2;
   int pingpong;
+  int one;      // always 1 (opaque to the compiler; see the TK form)
 };
 
-template <int PM, int SP>
+template <int PM, int SP, int TK>
 __global__ void __launch_bounds__(THREADS, 1) attn_ps_kernel(const __grid_constant__ CUtensorMap tmQKV, const PsParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -337,6 +338,20 @@ __global__ void __launch_bounds__(THREADS, 1) attn_ps_kernel(const __grid_consta
         } else if (!SP) {
           rescale_to(row_max());
         }
+        if (TK) {
+          // token-dense form: the scale / subtract of all 128 scores happens BEFORE the XU token is taken (ordered asm,
+          // so ptxas keeps it on this side of the barrier); what runs while holding the token is then a compact
+          // MUFU.EX2 stream (8 XU cycles per warp instruction) with only the pack / sum / store of the previous group
+          // in its shadow.  Intended regime: each warpgroup's non-XU work hides completely behind the other's token time.
+          const float2 c2 = make_float2(c, c);
+          const float2 nmc2 = make_float2(-m_ref * c, -m_ref * c);
+#pragma unroll
+          for (int i = 0; i < 64; ++i) {
+            const float2 a = ffma2_ordered(make_float2(s[2 * i], s[2 * i + 1]), c2, nmc2);
+            s[2 * i] = a.x;
+            s[2 * i + 1] = a.y;
+          }
+        }
         if (!pv_ready) named_bar_sync(5 + t, 160);          // the PV MMA that read the P buffer has finished
         pv_ready = true;
         if (pingpong) named_bar_sync(1 + t, 256);
@@ -352,6 +367,10 @@ __global__ void __launch_bounds__(THREADS, 1) attn_ps_kernel(const __grid_consta
           auto exp_group = [&](int g, float2 (&e)[8]) {
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
+              if (TK) {
+                e[q] = make_float2(ex2_ordered(s[16 * g + 2 * q]), ex2_ordered(s[16 * g + 2 * q + 1]));
+                continue;
+              }
               float2 a = ffma2(make_float2(s[16 * g + 2 * q], s[16 * g + 2 * q + 1]), c2, nmc2);
               if ((PM >> (q & 3)) & 1) {
                 if (SP) { a.x = fminf(a.x, 126.f); a.y = fminf(a.y, 126.f); }   // keep the exponent add of the polynomial in range
@@ -391,7 +410,15 @@ __global__ void __launch_bounds__(THREADS, 1) attn_ps_kernel(const __grid_consta
         // ptxas does not hoist this pass above the token barrier the way it hoists the eager form's (there it fills the
         // latency gaps of the FMNMX chain with FFMA2 / MUFU work), so with ping-pong on the two warpgroups' exponential
         // phases are strictly serial -- see profiles/README.md v8s.
-        float bsum = exp_pass();
+        float bsum = 0.f;
+        if (TK) {
+          // ptxas schedules arithmetic across BAR.SYNC freely (even `asm volatile`), so the MUFU stream is put into a
+          // loop with an opaque trip count of one: code inside a loop body is not hoisted above the barrier before it
+#pragma unroll 1
+          for (int rep = 0; rep < p.one; ++rep) bsum = exp_pass();
+        } else {
+          bsum = exp_pass();
+        }
         if (SP && it > 0 && __any_sync(0xffffffffu, !(bsum < 32768.f))) {
           rescale_to(row_max());          // a score outgrew the reference by 2^15 / 128 or more
           bsum = exp_pass();
@@ -439,14 +466,14 @@ __global__ void __launch_bounds__(THREADS, 1) attn_ps_kernel(const __grid_consta
   if (warp == MMA_WARP) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
-template <int PM, int SP>
+template <int PM, int SP, int TK>
 int launch_ps(cudaStream_t st, const CUtensorMap& tm, const PsParams& p, int ctas) {
   static bool configured = false;
   if (!configured) {
-    BG_CUDA(cudaFuncSetAttribute(attn_ps_kernel<PM, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    BG_CUDA(cudaFuncSetAttribute(attn_ps_kernel<PM, SP, TK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured = true;
   }
-  attn_ps_kernel<PM, SP><<<ctas, THREADS, SMEM_BYTES, st>>>(tm, p);
+  attn_ps_kernel<PM, SP, TK><<<ctas, THREADS, SMEM_BYTES, st>>>(tm, p);
   return check_launch("attn_ps_kernel launch");
 }
 
@@ -480,14 +507,21 @@ int launch_attention_persistent(cudaStream_t st, const AttnArgs& a, int poly) {
   p.scale_log2 = 1.4426950408889634f / 8.0f;
   const char* e1 = getenv("BG_ATTN_PP");
   p.pingpong = e1 ? atoi(e1) : 1;
+  p.one = 1;
   const int ctas = p.total < sms ? p.total : sms;
   static int spec = -1;                 // BG_ATTN_SPEC = 1: no row max after the first block (see SP in the kernel)
   if (spec < 0) {
     const char* e = getenv("BG_ATTN_SPEC");
     spec = e ? atoi(e) : 0;
   }
-  if (spec) return poly == 0 ? launch_ps<0x0, 1>(st, tm, p, ctas) : launch_ps<0x8, 1>(st, tm, p, ctas);
-  return poly == 0 ? launch_ps<0x0, 0>(st, tm, p, ctas) : launch_ps<0x8, 0>(st, tm, p, ctas);
+  static int dense = -1;                // BG_ATTN_TK = 1: scale / subtract before the XU token, MUFU-only stream inside it
+  if (dense < 0) {
+    const char* e = getenv("BG_ATTN_TK");
+    dense = e ? atoi(e) : 0;
+  }
+  if (dense) return launch_ps<0x0, 0, 1>(st, tm, p, ctas);      // no polynomial share, eager row max
+  if (spec) return poly == 0 ? launch_ps<0x0, 1, 0>(st, tm, p, ctas) : launch_ps<0x8, 1, 0>(st, tm, p, ctas);
+  return poly == 0 ? launch_ps<0x0, 0, 0>(st, tm, p, ctas) : launch_ps<0x8, 0, 0>(st, tm, p, ctas);
 }
 
 }  // namespace bg

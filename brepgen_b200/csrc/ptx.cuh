@@ -233,5 +233,19 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// volatile forms: keep their program order relative to barriers (which are volatile asm too), so that a block of
+// exponentials stays on its side of a named barrier instead of being scheduled across it
+__device__ __forceinline__ float ex2_ordered(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float2 ffma2_ordered(float2 a, float2 b, float2 c) {
+  uint64_t rd;
+  asm volatile("fma.rn.f32x2 %0, %1, %2, %3;"
+               : "=l"(rd)
+               : "l"(*reinterpret_cast<uint64_t*>(&a)), "l"(*reinterpret_cast<uint64_t*>(&b)), "l"(*reinterpret_cast<uint64_t*>(&c)));
+  return *reinterpret_cast<float2*>(&rd);
+}
 
 }  // namespace bg
