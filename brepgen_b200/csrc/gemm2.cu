@@ -13,6 +13,8 @@
 //   warp 2 (both)     : TMEM allocator (tcgen05.alloc.cta_group::2, 512 columns: accumulator double buffer)
 //   warps 4-11 (both) : epilogue (gemm_epilogue.cuh); all 512 epilogue threads of the pair arrive on the leader's
 //                       tmem-empty barrier (the peer through a cluster-mapped address)
+#include <stdlib.h>
+
 #include "bg_internal.h"
 #include "gemm_epilogue.cuh"
 #include "ptx.cuh"
@@ -66,6 +68,7 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 
+template <int PF>    // PF: residual loads of the epilogue pipelined one chunk ahead (gemm_epilogue_tile_pf)
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -171,7 +174,10 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int colbase = n_blk * BN + half * (BN / 2);
       mbar_wait(&tfull[acc], accphase);
       tc_fence_after();
-      gemm_epilogue_tile<CHUNKS>(p, tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN + half * (BN / 2), row0, colbase, xp, lane);
+      if (PF)
+        gemm_epilogue_tile_pf<CHUNKS>(p, tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN + half * (BN / 2), row0, colbase, xp, lane);
+      else
+        gemm_epilogue_tile<CHUNKS>(p, tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN + half * (BN / 2), row0, colbase, xp, lane);
       tc_fence_before();
       if (leader) mbar_arrive(&tempty[acc]);
       else mbar_arrive_cluster(&tempty[acc], 0);
@@ -189,15 +195,18 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 // N % 256 == 0 path of launch_gemm_f16 when BG_GEMM_2CTA != 0
 int launch_gemm2_f16(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p) {
-  static bool configured = false;
-  if (!configured) {
-    BG_CUDA(cudaFuncSetAttribute(gemm2_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    configured = true;
+  static int pf = -1;                   // BG_GEMM_PF = 1: prefetching residual epilogue (opt-in, not yet measured)
+  if (pf < 0) {
+    const char* e = getenv("BG_GEMM_PF");
+    pf = e ? atoi(e) : 0;
+    BG_CUDA(cudaFuncSetAttribute(gemm2_f16_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    BG_CUDA(cudaFuncSetAttribute(gemm2_f16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   }
   const int num_tiles = ((p.M + 255) / 256) * (p.N / BN);
   const int max_clusters = num_sms() / 2;
   const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
-  gemm2_f16_kernel<<<2 * clusters, 384, SMEM_BYTES, st>>>(tmA, tmB, p);
+  if (pf) gemm2_f16_kernel<1><<<2 * clusters, 384, SMEM_BYTES, st>>>(tmA, tmB, p);
+  else gemm2_f16_kernel<0><<<2 * clusters, 384, SMEM_BYTES, st>>>(tmA, tmB, p);
   return check_launch("gemm2_f16_kernel launch");
 }
 
