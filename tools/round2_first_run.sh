@@ -1,0 +1,13 @@
+#!/bin/bash
+# The measurements prepared at the end of round 1, one gpurun call (~3 min):
+#   gpurun --timeout 600 -- 'bash tools/round2_first_run.sh > gpurun_out/round2_first_run.log 2>&1'
+set -x
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/pipe_rates tools/pipe_rates.cu && /tmp/pipe_rates
+python tools/attn_check.py                                            # default kernel: parity + 716 TF/s at B = 64
+BG_ATTN_PS=1 python tools/attn_check.py                               # persistent: 711
+BG_ATTN_PS=1 BG_ATTN_TK=1 python tools/attn_check.py                  # token-dense exponential section (unmeasured)
+BG_ATTN_PS=1 BG_ATTN_TK=1 BG_ATTN_PP=0 python tools/attn_check.py     # same code without the token
+BG_ATTN_PS=1 BG_ATTN_SPEC=1 BG_ATTN_PP=0 python tools/attn_check.py   # no row max, no token (with the token: 537)
+BG_ATTN_PS=1 BG_ATTN_SPEC=1 BG_ATTN_PP=0 BG_ATTN_POLY=0 python tools/attn_check.py
+python tools/gemm_time.py                                             # 2-CTA GEMMs as measured in round 1
+BG_GEMM_PF=1 python tools/gemm_time.py                                # prefetching residual epilogue (unmeasured)
