@@ -359,6 +359,8 @@ __global__ void __launch_bounds__(THREADS, 1) attn_ps_kernel(const __grid_consta
         // one pass over the 128 scores of the row: p = exp2(c s - c m_ref), row sum (packed f32x2 math), fp16 P into the
         // K-major SW128 layout; software-pipelined by one 16-key group so that the MUFU.EX2 of group g are in flight while
         // group g-1 is summed, packed and stored.  Returns the block's row sum.
+        // the very last block of this CTA (tile 1, no next item) has nobody to hand the XU token to
+        const bool hand_over = pingpong && !(t == 1 && it == nblk - 1 && w_next >= p.total);
         auto exp_pass = [&]() -> float {
           const float2 c2 = make_float2(c, c);
           const float2 nmc2 = make_float2(-m_ref * c, -m_ref * c);
@@ -403,6 +405,9 @@ __global__ void __launch_bounds__(THREADS, 1) attn_ps_kernel(const __grid_consta
 #pragma unroll
             for (int q = 0; q < 8; ++q) eprev[q] = ecur[q];
           }
+          // TK: every MUFU.EX2 of this block has been issued -> the other warpgroup may start its stream; the pack / sum /
+          // store of the last group happen outside the token (no memory semantics are attached to the token barrier)
+          if (TK && hand_over) named_bar_arrive_relaxed(1 + (1 - t), 256);
           drain_group(7, eprev);
           return (acc.x + acc.y) + (acc1.x + acc1.y);
         };
@@ -423,8 +428,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_ps_kernel(const __grid_consta
           rescale_to(row_max());          // a score outgrew the reference by 2^15 / 128 or more
           bsum = exp_pass();
         }
-        // hand the XU token over; the very last block of this CTA (tile 1, no next item) has nobody to hand it to
-        if (pingpong && !(t == 1 && it == nblk - 1 && w_next >= p.total)) named_bar_arrive(1 + (1 - t), 256);
+        if (!TK && hand_over) named_bar_arrive(1 + (1 - t), 256);       // hand the XU token over
         tc_fence_before();                // orders the O rescale / the previous item's O read-out before the PV MMA
         fence_proxy_async_smem();         // generic-proxy writes of P -> visible to the tensor core (async proxy)
         mbar_arrive(&p_full[t]);

@@ -78,6 +78,11 @@ __device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads)
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// arrive without the compiler-level memory clobber: for barriers that only pass a scheduling token (no data hand-off)
+__device__ __forceinline__ void named_bar_arrive_relaxed(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads));
+}
+
 // ---------------------------------------------------------------- fences
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
