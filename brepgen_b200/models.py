@@ -118,10 +118,42 @@ class _Denoiser(nn.Module):
             ws = self._ws[key]
         return ws
 
+    # the C ABI takes raw pointers: every shape is checked here, against the reference's forward signatures
+    _X_WIDTH = {"surfpos": 6, "surfz": 48, "edgepos": 6, "edgez": 18}
+
+    def _check_shapes(self, x, surfPos, surfZ, edgePos, mask):
+        edge = self.kind in ("edgepos", "edgez")
+        want_dim = 4 if edge else 3
+        if x.dim() != want_dim or x.shape[-1] != self._X_WIDTH[self.kind]:
+            raise RuntimeError(f"{type(self).__name__}: expected a {want_dim}-D input with last dimension "
+                               f"{self._X_WIDTH[self.kind]}, got {tuple(x.shape)}")
+        B, S = x.shape[0], x.shape[1]
+        E = x.shape[2] if edge else 0
+        if B < 1 or S < 1 or (edge and E < 1):
+            raise RuntimeError(f"{type(self).__name__}: empty batch / face / edge dimension in {tuple(x.shape)}")
+
+        def need(name, t, shape):
+            if t is None:
+                raise RuntimeError(f"{type(self).__name__}: {name} is required")
+            if tuple(t.shape) != shape:
+                raise RuntimeError(f"{type(self).__name__}: {name} must have shape {shape}, got {tuple(t.shape)}")
+
+        if self.kind != "surfpos":
+            need("surfPos", surfPos, (B, S, 6))
+        if edge:
+            need("surfZ", surfZ, (B, S, 48))
+        if self.kind == "edgez":
+            need("edgePos", edgePos, (B, S, E, 6))
+        if mask is not None:
+            want = (B, S, E) if self.kind == "edgez" else (B, S)
+            if self.kind == "surfpos" or tuple(mask.shape) != want:
+                raise RuntimeError(f"{type(self).__name__}: mask must have shape {want}, got {tuple(mask.shape)}")
+
     # ---------------------------------------------------------------- shared forward plumbing
     def _run(self, x, timesteps, surfPos=None, surfZ=None, edgePos=None, mask=None, class_label=None, is_train=False):
         if is_train:
             raise RuntimeError("brepgen_b200 denoisers are inference-only (is_train=True is the reference's training path)")
+        self._check_shapes(x, surfPos, surfZ, edgePos, mask)
         if not x.is_cuda:
             raise RuntimeError("brepgen_b200 has no CPU path: inputs must be CUDA tensors on an sm_100 device")
         dev = x.device

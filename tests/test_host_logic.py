@@ -41,6 +41,26 @@ def test_state_dict_keys_and_load():
         NETS["surfpos"](False)(torch.zeros(1, 3, 6), torch.tensor([1]), None)   # no CPU path
 
 
+def test_forward_rejects_wrong_shapes_before_touching_the_device():
+    """the C ABI takes raw pointers, so the Python boundary validates every shape (no GPU needed to see the errors)"""
+    z = torch.zeros
+    cases = [
+        (NETS["surfpos"](False), (z(2, 5, 7), torch.tensor([1]), None)),                                  # last dim 6
+        (NETS["surfz"](False), (z(2, 5, 48), torch.tensor([1]), z(2, 4, 6), z(2, 5, dtype=torch.bool), None)),   # surfPos S
+        (NETS["surfz"](False), (z(2, 5, 48), torch.tensor([1]), z(2, 5, 6), z(2, 6, dtype=torch.bool), None)),   # mask S
+        (NETS["edgepos"](False), (z(2, 5, 3, 6), torch.tensor([1]), z(2, 5, 6), z(2, 5, 47), z(2, 5, dtype=torch.bool), None)),
+        (NETS["edgepos"](False), (z(2, 5, 6), torch.tensor([1]), z(2, 5, 6), z(2, 5, 48), z(2, 5, dtype=torch.bool), None)),
+        (NETS["edgez"](False), (z(2, 5, 3, 18), torch.tensor([1]), z(2, 5, 3, 6), z(2, 5, 6), z(2, 5, 48),
+                                z(2, 5, dtype=torch.bool), None)),                                          # per-edge mask
+        (NETS["edgez"](False), (z(0, 5, 3, 18), torch.tensor([1]), z(0, 5, 3, 6), z(0, 5, 6), z(0, 5, 48), None, None)),
+    ]
+    for m, args in cases:
+        with pytest.raises(RuntimeError, match="expected|must have shape|empty|required"):
+            m(*args)
+    with pytest.raises(RuntimeError, match="inference-only"):
+        NETS["surfpos"](False)(z(1, 3, 6), torch.tensor([1]), None, is_train=True)
+
+
 def test_sincos_table_matches_oracle():
     tab = reference_sincos_table()
     ref = O.sincos_embedding(torch.arange(1000))
