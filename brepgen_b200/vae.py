@@ -76,6 +76,10 @@ class _VaeModule(nn.Module):
         self._handle, self._sig = out, sig
 
     def forward(self, z: torch.Tensor) -> torch.Tensor:
+        want_dim = 4 if self.kind in (0, 2) else 3       # surface VAEs: (N,3,H,W); edge VAEs: (N,3,L)
+        if z.dim() != want_dim or z.shape[1] != 3 or z.shape[0] < 1:
+            raise RuntimeError(f"{type(self).__name__}: expected a non-empty {want_dim}-D tensor with 3 channels, "
+                               f"got {tuple(z.shape)}")
         if not z.is_cuda:
             raise RuntimeError("brepgen_b200 has no CPU path: z must be a CUDA tensor on an sm_100 device")
         dev = z.device

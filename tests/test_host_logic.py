@@ -59,6 +59,13 @@ def test_forward_rejects_wrong_shapes_before_touching_the_device():
             m(*args)
     with pytest.raises(RuntimeError, match="inference-only"):
         NETS["surfpos"](False)(z(1, 3, 6), torch.tensor([1]), None, is_train=True)
+    from brepgen_b200.vae import AutoencoderKL1DFastDecode, AutoencoderKLFastDecode
+    for vae, bad in ((AutoencoderKLFastDecode(), z(2, 4, 4, 4)), (AutoencoderKLFastDecode(), z(2, 3, 4)),
+                     (AutoencoderKL1DFastDecode(), z(2, 3, 4, 4)), (AutoencoderKL1DFastDecode(), z(0, 3, 4))):
+        with pytest.raises(RuntimeError, match="expected a non-empty"):
+            vae(bad)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        AutoencoderKLFastDecode()(z(2, 3, 4, 4))
 
 
 def test_sincos_table_matches_oracle():
