@@ -97,6 +97,13 @@ class DDPMScheduler:
         """x_{t-1}.  Extras over diffusers (all optional): `noise` = explicit N(0,1) tensor (parity runs),
         `model_output_uncond` + `guidance_w` = classifier-free combine fused into the step (sample.py:134),
         `out` = destination (may be `sample` for an in-place update)."""
+        # the C ABI takes raw pointers and one element count: every tensor must cover exactly sample.numel() elements
+        for name, ten in (("model_output", model_output), ("model_output_uncond", model_output_uncond), ("noise", noise),
+                          ("out", out)):
+            if ten is not None and tuple(ten.shape) != tuple(sample.shape):
+                raise RuntimeError(f"DDPMScheduler.step: {name} has shape {tuple(ten.shape)}, sample has {tuple(sample.shape)}")
+        if out is not None and (out.dtype != torch.float32 or not out.is_contiguous() or out.device != sample.device):
+            raise RuntimeError("DDPMScheduler.step: `out` must be a contiguous fp32 tensor on the sample's device")
         _require_cuda(sample, "sample")
         _require_cuda(model_output, "model_output")
         t = _as_int(timestep)
@@ -104,8 +111,6 @@ class DDPMScheduler:
         x = sample if (sample.dtype == torch.float32 and sample.is_contiguous()) else sample.float().contiguous()
         eps = model_output.float().contiguous()
         eps_u = None if model_output_uncond is None else model_output_uncond.float().contiguous()
-        if eps.shape != x.shape:
-            raise RuntimeError("model_output and sample must have the same shape")
         if noise is None and generator is not None and sigma != 0.0:
             noise = torch.randn(x.shape, generator=generator, device=x.device, dtype=torch.float32)
         if noise is not None:
@@ -195,6 +200,9 @@ class PNDMScheduler:
         return dst
 
     def step(self, model_output: torch.Tensor, timestep, sample: torch.Tensor, return_dict: bool = True):
+        if tuple(model_output.shape) != tuple(sample.shape):
+            raise RuntimeError(f"PNDMScheduler.step: model_output has shape {tuple(model_output.shape)}, "
+                               f"sample has {tuple(sample.shape)}")
         _require_cuda(sample, "sample")
         _require_cuda(model_output, "model_output")
         t = _as_int(timestep)

@@ -68,6 +68,23 @@ def test_forward_rejects_wrong_shapes_before_touching_the_device():
         AutoencoderKLFastDecode()(z(2, 3, 4, 4))
 
 
+def test_scheduler_steps_reject_mismatched_tensors():
+    x = torch.zeros(2, 5, 6)
+    d, p = DDPMScheduler(clip_sample=True, clip_sample_range=3), PNDMScheduler()
+    with pytest.raises(RuntimeError, match="model_output has shape"):
+        d.step(torch.zeros(2, 5, 7), 10, x)
+    with pytest.raises(RuntimeError, match="noise has shape"):
+        d.step(torch.zeros(2, 5, 6), 10, x, noise=torch.zeros(2, 5))
+    with pytest.raises(RuntimeError, match="model_output_uncond has shape"):
+        d.step(torch.zeros(2, 5, 6), 10, x, model_output_uncond=torch.zeros(1, 5, 6), guidance_w=0.6)
+    with pytest.raises(RuntimeError, match="`out` must be"):
+        d.step(torch.zeros(2, 5, 6), 10, x, out=torch.zeros(2, 5, 6, dtype=torch.float16))
+    with pytest.raises(RuntimeError, match="model_output has shape"):
+        p.step(torch.zeros(2, 5, 7), 995, x)
+    with pytest.raises(RuntimeError):           # well-formed CPU tensors: there is no CPU path
+        d.step(torch.zeros(2, 5, 6), 10, x)
+
+
 def test_sincos_table_matches_oracle():
     tab = reference_sincos_table()
     ref = O.sincos_embedding(torch.arange(1000))
