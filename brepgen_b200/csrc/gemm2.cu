@@ -198,9 +198,10 @@ int launch_gemm2_f16(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap&
   static int pf = -1;                   // BG_GEMM_PF = 1: prefetching residual epilogue (opt-in, not yet measured)
   if (pf < 0) {
     const char* e = getenv("BG_GEMM_PF");
-    pf = e ? atoi(e) : 0;
-    BG_CUDA(cudaFuncSetAttribute(gemm2_f16_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    BG_CUDA(cudaFuncSetAttribute(gemm2_f16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    const int want = (e && atoi(e) != 0) ? 1 : 0;
+    if (want) BG_CUDA(cudaFuncSetAttribute(gemm2_f16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    else BG_CUDA(cudaFuncSetAttribute(gemm2_f16_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    pf = want;                          // only after the attribute call succeeded
   }
   const int num_tiles = ((p.M + 255) / 256) * (p.N / BN);
   const int max_clusters = num_sms() / 2;
