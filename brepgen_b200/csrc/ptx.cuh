@@ -238,8 +238,9 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// volatile forms: keep their program order relative to barriers (which are volatile asm too), so that a block of
-// exponentials stays on its side of a named barrier instead of being scheduled across it
+// volatile forms: NVVM keeps their order relative to other volatile asm (barriers included).  That only fixes the PTX
+// order -- ptxas still schedules arithmetic across BAR.SYNC when both sit in one basic block (seen in SASS), which is
+// why attn_ps.cu additionally puts its MUFU stream into a loop with an opaque trip count of one
 __device__ __forceinline__ float ex2_ordered(float x) {
   float y;
   asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
