@@ -369,8 +369,9 @@ __global__ void __launch_bounds__(THREADS, 1) attn_ps_kernel(const __grid_consta
           auto exp_group = [&](int g, float2 (&e)[8]) {
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-              if (TK) {
-                e[q] = make_float2(ex2_ordered(s[16 * g + 2 * q]), ex2_ordered(s[16 * g + 2 * q + 1]));
+              if (TK) {   // s[] already holds c s - c m_ref; the polynomial share (FMA pipe) rides in the MUFU stream's shadow
+                if ((PM >> (q & 3)) & 1) e[q] = exp2_poly2(make_float2(s[16 * g + 2 * q], s[16 * g + 2 * q + 1]));
+                else e[q] = make_float2(ex2_ordered(s[16 * g + 2 * q]), ex2_ordered(s[16 * g + 2 * q + 1]));
                 continue;
               }
               float2 a = ffma2(make_float2(s[16 * g + 2 * q], s[16 * g + 2 * q + 1]), c2, nmc2);
@@ -523,7 +524,7 @@ int launch_attention_persistent(cudaStream_t st, const AttnArgs& a, int poly) {
     const char* e = getenv("BG_ATTN_TK");
     dense = e ? atoi(e) : 0;
   }
-  if (dense) return launch_ps<0x0, 0, 1>(st, tm, p, ctas);      // no polynomial share, eager row max
+  if (dense) return poly == 0 ? launch_ps<0x0, 0, 1>(st, tm, p, ctas) : launch_ps<0x8, 0, 1>(st, tm, p, ctas);   // eager row max
   if (spec) return poly == 0 ? launch_ps<0x0, 1, 0>(st, tm, p, ctas) : launch_ps<0x8, 1, 0>(st, tm, p, ctas);
   return poly == 0 ? launch_ps<0x0, 0, 0>(st, tm, p, ctas) : launch_ps<0x8, 0, 0>(st, tm, p, ctas);
 }

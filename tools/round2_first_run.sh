@@ -5,7 +5,8 @@ set -x
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/pipe_rates tools/pipe_rates.cu && /tmp/pipe_rates
 python tools/attn_check.py                                            # default kernel: parity + 716 TF/s at B = 64
 BG_ATTN_PS=1 python tools/attn_check.py                               # persistent: 711
-BG_ATTN_PS=1 BG_ATTN_TK=1 python tools/attn_check.py                  # token-dense exponential section (unmeasured)
+BG_ATTN_PS=1 BG_ATTN_TK=1 BG_ATTN_POLY=0 python tools/attn_check.py   # token-dense exponential section, MUFU only (unmeasured)
+BG_ATTN_PS=1 BG_ATTN_TK=1 python tools/attn_check.py                  # ... with 25 % of the exponentials on the FMA pipe
 BG_ATTN_PS=1 BG_ATTN_TK=1 BG_ATTN_PP=0 python tools/attn_check.py     # same code without the token
 BG_ATTN_PS=1 BG_ATTN_SPEC=1 BG_ATTN_PP=0 python tools/attn_check.py   # no row max, no token (with the token: 537)
 BG_ATTN_PS=1 BG_ATTN_SPEC=1 BG_ATTN_PP=0 BG_ATTN_POLY=0 python tools/attn_check.py
