@@ -12,3 +12,6 @@ BG_ATTN_PS=1 BG_ATTN_SPEC=1 BG_ATTN_PP=0 python tools/attn_check.py   # no row m
 BG_ATTN_PS=1 BG_ATTN_SPEC=1 BG_ATTN_PP=0 BG_ATTN_POLY=0 python tools/attn_check.py
 python tools/gemm_time.py                                             # 2-CTA GEMMs as measured in round 1
 BG_GEMM_PF=1 python tools/gemm_time.py                                # prefetching residual epilogue (unmeasured)
+BG_GEMM_PF=2 python tools/gemm_time.py                                # TMA-staged residual epilogue (unmeasured, never run)
+BG_GEMM_PF=2 python -m pytest tests/test_gpu_ops.py -q -k gemm         # ... its parity incl. ragged M and in-place residual
+BG_GEMM_PF=2 python -m pytest tests/test_gpu_denoisers.py -q -k "vs_oracle"
