@@ -37,3 +37,20 @@ def test_sincos_matches_reference():
     assert np.abs(y - GOLD["sincos|surfpos"]).max() < 1e-6
     # cos block first, then sin (network.py:1060)
     assert np.allclose(y[0, :384], 1.0) and np.allclose(y[0, 384:], 0.0)
+
+
+def test_dedup_oracle_matches_reference_statements():
+    """oracle/cascade.py dedup loops vs the outputs of the reference's own statements (sample.py:159-183, :242-261),
+    executed verbatim by tests/golden/make_golden_dedup.py: packed boxes and both masks must be IDENTICAL."""
+    from oracle.cascade import dedup_edges_np, dedup_surfaces_np
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "dedup_golden.npz"))
+    n = len([k for k in gold.files if k.endswith("_surfPos_in")])
+    assert n >= 5
+    for i in range(n):
+        sp = gold[f"c{i}_surfPos_in"]
+        pos, mask = dedup_surfaces_np(sp, 0.08)
+        assert np.array_equal(mask, gold[f"c{i}_surfMask"]), i
+        assert np.array_equal(pos, gold[f"c{i}_surfPos_out"]), i
+        em = dedup_edges_np(gold[f"c{i}_edgePos_in"], mask, 0.08)
+        assert np.array_equal(em, gold[f"c{i}_edgeM"]), i
+        assert mask.shape == sp.shape[:2] and em.shape == gold[f"c{i}_edgePos_in"].shape[:3]
