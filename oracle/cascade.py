@@ -56,10 +56,14 @@ def dedup_edges_np(edgePos: np.ndarray, surfMask: np.ndarray, thr: float):
     return edgeM
 
 
-def run_cascade(sds, cfg, init_noise, step_noise):
+def run_cascade(sds, cfg, init_noise, step_noise, forwards=None, surf_vae=None, edge_vae=None):
     """sds: {'surfpos','surfz','edgepos','edgez'} state dicts; cfg: brepgen_b200.sampler.CascadeConfig-like object;
     init_noise: dict name -> tensor; step_noise(stage, i, shape) -> tensor (DDPM noise injected at step i).
-    Only the 'ddpm' schedule and the 'reference' hybrid for non-CFG / CFG are restated."""
+    Only the 'ddpm' schedule and the 'reference' hybrid for non-CFG / CFG are restated.
+    forwards: optional {'surfpos','surfz','edgepos','edgez'} callables with the reference's forward signatures, used
+    instead of the oracle denoisers (the driver itself is pinned this way against the reference's own statements executed
+    around cheap stand-in networks, tests/golden/make_golden_driver.py).  surf_vae / edge_vae: optional decoders; when
+    given, the decode input preparation of sample.py:289-293 is restated too (outputs 'surf_ncs', 'edge_ncs')."""
     B, S0, E = cfg.batch_size, cfg.num_surfaces, cfg.num_edges
     w = cfg.guidance_w
     label2 = None
@@ -106,9 +110,16 @@ def run_cascade(sds, cfg, init_noise, step_noise):
             return x.repeat(1, 2, 1)
         return x
 
+    if forwards is None:
+        forwards = {"surfpos": lambda *a: O.surfpos_forward(sds["surfpos"], *a),
+                    "surfz": lambda *a: O.surfz_forward(sds["surfz"], *a),
+                    "edgepos": lambda *a: O.edgepos_forward(sds["edgepos"], *a),
+                    "edgez": lambda *a: O.edgez_forward(sds["edgez"], *a)}
+    F = forwards
+
     with torch.no_grad():
         surfPos = stage("surfPos", init_noise["surfPos"].clone(),
-                        lambda x, t: O.surfpos_forward(sds["surfpos"], x, t, label2), True, late_increase)
+                        lambda x, t: F["surfpos"](x, t, label2), True, late_increase)
         if not state["late"]:
             surfPos = surfPos.repeat(1, 2, 1)
         S = surfPos.shape[1]
@@ -119,17 +130,25 @@ def run_cascade(sds, cfg, init_noise, step_noise):
             surfPos, surfMask = torch.from_numpy(p), torch.from_numpy(m)
         sP, sM = rep2(surfPos), rep2(surfMask)
         surfZ = stage("surfZ", init_noise["surfZ"].clone(),
-                      lambda x, t: O.surfz_forward(sds["surfz"], x, t, sP, sM, label2), False)
+                      lambda x, t: F["surfz"](x, t, sP, sM, label2), False)
         sZ = rep2(surfZ)
         edgePos = stage("edgePos", init_noise["edgePos"].clone(),
-                        lambda x, t: O.edgepos_forward(sds["edgepos"], x, t, sP, sZ, sM, label2), True)
+                        lambda x, t: F["edgepos"](x, t, sP, sZ, sM, label2), True)
         if cfg.dense_masks:
             edgeM = torch.zeros(B, S, E, dtype=torch.bool)
         else:
             edgeM = torch.from_numpy(dedup_edges_np(edgePos.numpy(), surfMask.numpy(), np.float32(cfg.bbox_threshold)))
         eP, eM = rep2(edgePos), rep2(edgeM)
         edgeZV = stage("edgeZV", init_noise["edgeZV"].clone(),
-                       lambda x, t: O.edgez_forward(sds["edgez"], x, t, eP, sP, sZ, eM, label2), False)
+                       lambda x, t: F["edgez"](x, t, eP, sP, sZ, eM, label2), False)
         edgeZV = edgeZV.masked_fill(edgeM.unsqueeze(-1), 0.0)
-    return {"surfPos": surfPos / 3.0, "surfMask": surfMask, "surfZ": surfZ, "edgePos": edgePos / 3.0, "edgeM": edgeM,
-            "edge_z": edgeZV[..., :12], "edgeV": edgeZV[..., 12:]}
+        out = {"surfPos": surfPos / 3.0, "surfMask": surfMask, "surfZ": surfZ, "edgePos": edgePos / 3.0, "edgeM": edgeM,
+               "edge_z": edgeZV[..., :12], "edgeV": edgeZV[..., 12:]}
+        # decoder inputs (sample.py:289-293): 48 = 16 positions x 3 channels -> (N,3,4,4); 12 = 4 x 3 -> (N,3,4)
+        if surf_vae is not None:
+            z = surfZ.unflatten(-1, (16, 3)).flatten(0, 1).permute(0, 2, 1).unflatten(-1, (4, 4))
+            out["surf_ncs"] = surf_vae(z).permute(0, 2, 3, 1).unflatten(0, (B, S))
+        if edge_vae is not None:
+            z = out["edge_z"].unflatten(-1, (4, 3)).reshape(-1, 4, 3).permute(0, 2, 1)
+            out["edge_ncs"] = edge_vae(z).permute(0, 2, 1).reshape(B, S, E, 32, 3)
+    return out
