@@ -28,3 +28,28 @@ def test_cubic_upsampler_partition_of_unity_and_ramp():
     ramp = torch.arange(16.0).view(1, 1, 16)
     y = V.cubic_upsample1d(ramp, k)[0, 0, 8:24]          # interior: half-sample-phase ramp
     assert torch.allclose(y[1:] - y[:-1], torch.full((15,), 0.5), atol=1e-5)
+
+
+def test_edge_decoder_oracle_matches_reference_wrapper_classes():
+    """oracle edge_decode vs the outputs of the reference's OWN AutoencoderKL1DFastDecode / Decoder1D / UNetMidBlock1D /
+    UpBlock1D (network.py:786-858, :188-299, :51-83, :30-48), instantiated with sample.py:86-97's arguments over module
+    forms of the three diffusers leaves by tests/golden/make_golden_vae1d.py (which also checks the 193 state-dict keys and
+    shapes of brepgen_b200.spec.edge_decoder_spec against that module tree).  Pins the wrapper the reference owns; the
+    arithmetic inside the diffusers leaves stays unpinned."""
+    import os
+    import sys
+    import numpy as np
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_golden_vae1d as G
+    from brepgen_b200.spec import edge_decoder_spec
+    from brepgen_b200.synth import synth_state_dict
+    from oracle import vae as V
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "vae1d_golden.npz"))
+    sd = synth_state_dict(edge_decoder_spec(), seed=2)
+    for seed, n in ((0, 3), (1, 7)):
+        with torch.no_grad():
+            y = V.edge_decode(sd, G.inputs(seed, n)).numpy()
+        ref = gold[f"s{seed}"]
+        assert y.shape == ref.shape
+        err = float(np.linalg.norm(y - ref) / np.linalg.norm(ref))
+        assert err < 1e-5, err
