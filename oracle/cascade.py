@@ -4,6 +4,11 @@ sample.py itself cannot be imported here (it imports OpenCASCADE at :9 and hard-
 loop is restated device-agnostically around the oracle denoisers (oracle/denoisers.py, pinned to the reference's own
 classes) and the oracle schedulers (oracle/schedulers.py, parity unpinned).  The de-duplication loops follow
 sample.py:159-183 and :242-261 statement by statement (numpy, fp32).
+
+Pinned: tests/golden/dedup_golden.npz and tests/golden/driver_golden.npz hold outputs of the reference's OWN statements
+(sample.py:159-183, :242-261 and the whole sampling block :122-299), which tests/golden/make_golden_dedup.py and
+make_golden_driver.py read from the reference file and exec() verbatim (the driver around stand-in networks and the
+oracle schedulers); tests/test_oracle_golden.py requires identical masks and matching tensors from this restatement.
 """
 from __future__ import annotations
 
