@@ -140,6 +140,24 @@ def test_pndm_transfer_is_ddim():
         assert torch.allclose(cs * xt - ce * eps, ref, atol=5e-4)
 
 
+def test_initial_noise_matches_reference_randn_tensor():
+    """the four initial-noise draws of brepgen_b200/sampler.py (CPU generator seeded with cfg.seed, order surfPos, surfZ,
+    edgePos, edgeZV) vs the reference's own randn_tensor (utils.py:60-97, exec()ed by tests/golden/make_golden_randn.py)
+    under torch.manual_seed(seed): bit-identical"""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_golden_randn as G
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "randn_golden.npz"))
+    gen = torch.Generator().manual_seed(G.SEED)
+    for name, shape in G.SHAPES.items():
+        assert np.array_equal(torch.randn(shape, generator=gen).numpy(), gold[name]), name
+    # and the sampler draws them exactly like this, in this order
+    src = open(os.path.join(ROOT, "brepgen_b200", "sampler.py")).read()
+    assert "cpu_gen = torch.Generator().manual_seed(cfg.seed)" in src and "torch.randn(shape, generator=cpu_gen)" in src
+    order = [src.index(f'noise("{n}"') for n in G.SHAPES]
+    assert order == sorted(order)
+
+
 def test_shard_batch_partitions():
     for gb in (1, 7, 256, 2048):
         for ws in (1, 2, 3, 8):
