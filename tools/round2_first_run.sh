@@ -3,7 +3,7 @@
 #   gpurun --timeout 600 -- 'bash tools/round2_first_run.sh > gpurun_out/round2_first_run.log 2>&1'
 set -x
 # tests added after the round-1 GPU budget ended (the driver one is xfail(strict=False) until it has passed once)
-python -m pytest tests/test_gpu_zz_dedup_golden.py tests/test_gpu_zz_driver_golden.py -q -rxX
+python -m pytest tests/test_gpu_zz_dedup_golden.py tests/test_gpu_zz_driver_golden.py tests/test_gpu_zz_config1_surfpos.py -q -rxX -s
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/pipe_rates tools/pipe_rates.cu && /tmp/pipe_rates
 python tools/attn_check.py                                            # default kernel: parity + 716 TF/s at B = 64
 BG_ATTN_PS=1 python tools/attn_check.py                               # persistent: 711
