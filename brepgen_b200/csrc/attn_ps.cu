@@ -56,6 +56,7 @@ struct PsParams {
   float scale_log2;
   int pingpong;
   int one;      // always 1 (opaque to the compiler; see the TK form)
+  int stagger;  // ns that warpgroup 1 sleeps once before its first block (anti-phase start without a token; 0 = off)
 };
 
 template <int PM, int SP, int TK>
@@ -258,6 +259,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_ps_kernel(const __grid_consta
       ld_words(w / per_sample, 0, nxt);
       if (pingpong && t == 1) named_bar_arrive(1, 256);    // tile 0 owns the XU token first
     }
+    if (t == 1 && p.stagger > 0) __nanosleep((unsigned)p.stagger);
     while (w < p.total) {
       const int qg = w % p.nqg, hb = w / p.nqg, h = hb % NHEAD, b = hb / NHEAD;
       // candidate next item: its block count is requested now and consumed in the last block of this item
@@ -513,6 +515,8 @@ int launch_attention_persistent(cudaStream_t st, const AttnArgs& a, int poly) {
   const char* e1 = getenv("BG_ATTN_PP");
   p.pingpong = e1 ? atoi(e1) : 1;
   p.one = 1;
+  const char* e2 = getenv("BG_ATTN_STAGGER");   // experiment: start warpgroup 1 this many ns late (use with BG_ATTN_PP=0)
+  p.stagger = e2 ? atoi(e2) : 0;
   const int ctas = p.total < sms ? p.total : sms;
   static int spec = -1;                 // BG_ATTN_SPEC = 1: no row max after the first block (see SP in the kernel)
   if (spec < 0) {

@@ -10,6 +10,7 @@ BG_ATTN_PS=1 python tools/attn_check.py                               # persiste
 BG_ATTN_PS=1 BG_ATTN_TK=1 BG_ATTN_POLY=0 python tools/attn_check.py   # token-dense exponential section, MUFU only (unmeasured)
 BG_ATTN_PS=1 BG_ATTN_TK=1 python tools/attn_check.py                  # ... with 25 % of the exponentials on the FMA pipe
 BG_ATTN_PS=1 BG_ATTN_TK=1 BG_ATTN_PP=0 python tools/attn_check.py     # same code without the token
+BG_ATTN_PS=1 BG_ATTN_PP=0 BG_ATTN_STAGGER=800 python tools/attn_check.py  # eager form, no token, warpgroup 1 starts 0.8 us late
 BG_ATTN_PS=1 BG_ATTN_SPEC=1 BG_ATTN_PP=0 python tools/attn_check.py   # no row max, no token (with the token: 537)
 BG_ATTN_PS=1 BG_ATTN_SPEC=1 BG_ATTN_PP=0 BG_ATTN_POLY=0 python tools/attn_check.py
 python tools/gemm_time.py                                             # 2-CTA GEMMs as measured in round 1
