@@ -13,8 +13,8 @@ and is anchored on: input/output shapes consumed at sample.py:289-294, the state
 Partly pinned since: the EDGE decoder's wrapper -- everything the reference itself defines (AutoencoderKL1DFastDecode,
 Decoder1D, UNetMidBlock1D, UpBlock1D: block order and counts, channel wiring, head count, norms, key names) -- is checked
 against outputs of those classes (tests/golden/vae1d_golden.npz, made by tests/golden/make_golden_vae1d.py from the real
-network.py over module forms of the three diffusers leaves).  The arithmetic inside the diffusers leaves and the whole
-2-D decoder / both encoders remain unpinned.
+network.py over module forms of the diffusers leaves), and the EDGE encoder's wrapper (AutoencoderKL1DFastEncode,
+Encoder1D) the same way.  The arithmetic inside the diffusers leaves and the whole 2-D decoder / encoder remain unpinned.
 """
 from __future__ import annotations
 

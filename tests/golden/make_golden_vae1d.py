@@ -101,6 +101,52 @@ class Upsample1d(nn.Module):
         return F.conv_transpose1d(hidden_states, weight, stride=2, padding=self.pad * 2 + 1)
 
 
+class Downsample1d(nn.Module):
+    def __init__(self, kernel="linear", pad_mode="reflect"):
+        super().__init__()
+        assert kernel == "cubic"
+        self.pad_mode = pad_mode
+        kernel_1d = torch.tensor(CUBIC)
+        self.pad = kernel_1d.shape[0] // 2 - 1
+        self.register_buffer("kernel", kernel_1d)
+
+    def forward(self, hidden_states):
+        hidden_states = F.pad(hidden_states, (self.pad,) * 2, self.pad_mode)
+        weight = hidden_states.new_zeros([hidden_states.shape[1], hidden_states.shape[1], self.kernel.shape[0]])
+        idx = torch.arange(hidden_states.shape[1])
+        weight[idx, idx] = self.kernel.to(weight)
+        return F.conv1d(hidden_states, weight, stride=2)
+
+
+class DownBlock1D(nn.Module):
+    def __init__(self, out_channels, in_channels, mid_channels=None):
+        super().__init__()
+        mid_channels = out_channels if mid_channels is None else mid_channels
+        self.down = Downsample1d("cubic")
+        self.resnets = nn.ModuleList([ResConvBlock(in_channels, mid_channels, mid_channels),
+                                      ResConvBlock(mid_channels, mid_channels, mid_channels),
+                                      ResConvBlock(mid_channels, mid_channels, out_channels)])
+
+    def forward(self, hidden_states, temb=None):
+        hidden_states = self.down(hidden_states)
+        for resnet in self.resnets:
+            hidden_states = resnet(hidden_states)
+        return hidden_states, (hidden_states,)
+
+
+def get_down_block(down_block_type, num_layers, in_channels, out_channels, temb_channels, add_downsample):
+    assert down_block_type == "DownBlock1D"
+    return DownBlock1D(out_channels=out_channels, in_channels=in_channels)
+
+
+class DiagonalGaussianDistribution:
+    def __init__(self, parameters, deterministic=False):
+        self.mean, self.logvar = torch.chunk(parameters, 2, dim=1)
+
+    def mode(self):
+        return self.mean
+
+
 class DecoderOutput:
     def __init__(self, sample):
         self.sample = sample
@@ -110,8 +156,10 @@ def load_reference_network_with_leaves():
     import make_golden as MG
     MG._stub_diffusers()
     sys.modules["diffusers.models.unets.unet_1d_blocks"].__dict__.update(
-        ResConvBlock=ResConvBlock, SelfAttention1d=SelfAttention1d, Upsample1d=Upsample1d)
-    sys.modules["diffusers.models.autoencoders.vae"].__dict__.update(DecoderOutput=DecoderOutput)
+        ResConvBlock=ResConvBlock, SelfAttention1d=SelfAttention1d, Upsample1d=Upsample1d, get_down_block=get_down_block)
+    sys.modules["diffusers.models.autoencoders.vae"].__dict__.update(
+        DecoderOutput=DecoderOutput, DiagonalGaussianDistribution=DiagonalGaussianDistribution)
+    sys.modules["diffusers.utils"].__dict__.update(BaseOutput=object)
     sys.modules.pop("network", None)
     sys.path.insert(0, MG.REF)
     import network
@@ -121,6 +169,10 @@ def load_reference_network_with_leaves():
 
 def inputs(seed, n):
     return torch.randn(n, 3, 4, generator=torch.Generator().manual_seed(seed))
+
+
+def enc_inputs(seed, n):
+    return torch.rand(n, 3, 32, generator=torch.Generator().manual_seed(100 + seed)) * 2 - 1
 
 
 def main():
@@ -143,6 +195,23 @@ def main():
         with torch.no_grad():
             out[f"s{seed}"] = vae(inputs(seed, n)).numpy().astype(np.float32)
         print("case", seed, out[f"s{seed}"].shape, float(np.abs(out[f"s{seed}"]).max()))
+    # the encoder of BASELINE config 1's edge analogue: AutoencoderKL1DFastEncode (network.py:690-783) over Encoder1D
+    # (:86-185, the reference's own) with the constructor arguments of trainer.py:841-852; its down blocks are diffusers'
+    from brepgen_b200.spec import edge_encoder_spec
+    enc = network.AutoencoderKL1DFastEncode(
+        in_channels=3, out_channels=3,
+        down_block_types=["DownBlock1D", "DownBlock1D", "DownBlock1D"], up_block_types=["UpBlock1D", "UpBlock1D", "UpBlock1D"],
+        block_out_channels=[128, 256, 512], layers_per_block=2, act_fn="silu", latent_channels=3, norm_num_groups=32,
+        sample_size=512)
+    sde = synth_state_dict(edge_encoder_spec(), seed=3)
+    enc_keys = {k: tuple(v.shape) for k, v in enc.state_dict().items()}
+    assert enc_keys == {k: tuple(v.shape) for k, v in sde.items()}, set(enc_keys) ^ set(sde)
+    enc.load_state_dict(sde)
+    enc.eval()
+    for seed, n in ((0, 2), (1, 5)):
+        with torch.no_grad():
+            out[f"enc_s{seed}"] = enc(enc_inputs(seed, n)).numpy().astype(np.float32)
+        print("encoder case", seed, out[f"enc_s{seed}"].shape, float(np.abs(out[f"enc_s{seed}"]).max()))
     path = os.path.join(ROOT, "tests", "golden", "vae1d_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes; keys checked:", len(ref_keys))

@@ -53,3 +53,14 @@ def test_edge_decoder_oracle_matches_reference_wrapper_classes():
         assert y.shape == ref.shape
         err = float(np.linalg.norm(y - ref) / np.linalg.norm(ref))
         assert err < 1e-5, err
+    # the edge ENCODER wrapper the same way: AutoencoderKL1DFastEncode / Encoder1D (network.py:690-783, :86-185) with
+    # trainer.py:841-852's arguments; 193 keys of edge_encoder_spec loaded strictly by the generator
+    from brepgen_b200.spec import edge_encoder_spec
+    sde = synth_state_dict(edge_encoder_spec(), seed=3)
+    for seed, n in ((0, 2), (1, 5)):
+        with torch.no_grad():
+            y = V.edge_encode(sde, G.enc_inputs(seed, n)).numpy()
+        ref = gold[f"enc_s{seed}"]
+        assert y.shape == ref.shape
+        err = float(np.linalg.norm(y - ref) / np.linalg.norm(ref))
+        assert err < 1e-5, err
