@@ -3,7 +3,7 @@
 
     python bench.py --gpus 1 --steps 3 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
-    python bench.py --impl reference ...        # the reference's algorithm on the host cores (oracle port), same metric
+    python bench.py --impl reference ...        # the reference's own classes on the host cores (baseline/_ref), same metric
 
 Workload (BASELINE.json configs[2]): full ABC cascade, batch 256 per GPU, S0 = 50 -> S = 100 faces,
 E = 40 edges/face (edge-stage sequences of 4000 tokens), dense masks, random-init weights, Gaussian inputs.
@@ -80,35 +80,54 @@ def cascade_flops_per_brep(S0, S, E, steps=1000):
     return steps * (0.75 * sp(S0) + 0.25 * sp(S) + sz + ep + ez)
 
 
-# ------------------------------------------------------------------------------------------------ CPU baseline (oracle port)
-def cpu_reference_sample(S0, S, E, reps, threads=None, inner_warm=True):
-    """Times the oracle (CPU fp32 restatement of the reference, pinned to its own classes) on the host cores: per stage,
-    one forward + scheduler step at batch 1, `reps` timed repetitions after one warm-up; extrapolated to the
-    4 x 1000-step cascade.  Returns (B-reps/s, cores, description)."""
+# ------------------------------------------------------------------------------------------------ CPU baseline
+def cpu_reference_sample(S0, S, E, reps, threads=None, inner_warm=True, kind="auto"):
+    """Times the reference's algorithm for this path on the host cores: per stage, one network forward + DDPM scheduler
+    step at batch 1, `reps` timed repetitions after one warm-up; extrapolated to the 4 x 1000-step cascade.
+
+    kind = "reference": the reference's OWN classes (SurfPosNet ... EdgeZNet of network.py:1066-1393, stock code path:
+    nn.TransformerEncoder etc., eval(), no_grad), imported unmodified from baseline/_ref/network.py (or /root/reference)
+    through oracle/reference_loader.py; "port": oracle/denoisers.py (the pinned restatement); "auto": the reference when
+    its file is present, else the port.  The scheduler step is oracle/schedulers.py in both cases (diffusers is absent
+    offline; the step is < 0.1 % of the time).  Returns (B-reps/s, cores, description, kind_used)."""
     from brepgen_b200.spec import denoiser_spec
     from brepgen_b200.synth import synth_state_dict
     from oracle import denoisers as O
+    from oracle.reference_loader import load_reference_network
     from oracle.schedulers import DDPMOracle
 
     cores = threads or (os.cpu_count() or 1)
     torch.set_num_threads(cores)
+    net = load_reference_network(required=False) if kind in ("auto", "reference") else None
+    if kind == "reference" and net is None:
+        raise RuntimeError("reference classes requested but neither baseline/_ref/network.py nor /root/reference exists")
+    used = "reference" if net is not None else "port"
+    ref_cls = None if net is None else {"surfpos": net.SurfPosNet, "surfz": net.SurfZNet, "edgepos": net.EdgePosNet,
+                                        "edgez": net.EdgeZNet}
     orc = DDPMOracle()
     g = torch.Generator().manual_seed(0)
     r = lambda *s: torch.randn(*s, generator=g)
     t = torch.tensor([500])
     per = {}
     with torch.no_grad():
-        for name, kind, shape in (("surfpos@S0", "surfpos", (1, S0, 6)), ("surfpos@S", "surfpos", (1, S, 6)),
-                                  ("surfz", "surfz", (1, S, 48)), ("edgepos", "edgepos", (1, S, E, 6)),
-                                  ("edgez", "edgez", (1, S, E, 18))):
-            sd = synth_state_dict(denoiser_spec(kind, False), seed=1)
+        for name, knd, shape in (("surfpos@S0", "surfpos", (1, S0, 6)), ("surfpos@S", "surfpos", (1, S, 6)),
+                                 ("surfz", "surfz", (1, S, 48)), ("edgepos", "edgepos", (1, S, E, 6)),
+                                 ("edgez", "edgez", (1, S, E, 18))):
+            sd = synth_state_dict(denoiser_spec(knd, False), seed=1)
             x = r(*shape)
             sP, sZ, eP = r(1, shape[1], 6), r(1, shape[1], 48), r(1, shape[1], E, 6)
             fm = torch.zeros(1, shape[1], dtype=torch.bool)
             em = torch.zeros(1, shape[1], E, dtype=torch.bool)
-            fwd = {"surfpos": lambda: O.surfpos_forward(sd, x, t), "surfz": lambda: O.surfz_forward(sd, x, t, sP, fm),
-                   "edgepos": lambda: O.edgepos_forward(sd, x, t, sP, sZ, fm),
-                   "edgez": lambda: O.edgez_forward(sd, x, t, eP, sP, sZ, em)}[kind]
+            if ref_cls is not None:
+                m = ref_cls[knd](False)
+                m.load_state_dict(sd)
+                m.eval()
+                fwd = {"surfpos": lambda: m(x, t, None), "surfz": lambda: m(x, t, sP, fm, None),
+                       "edgepos": lambda: m(x, t, sP, sZ, fm, None), "edgez": lambda: m(x, t, eP, sP, sZ, em, None)}[knd]
+            else:
+                fwd = {"surfpos": lambda: O.surfpos_forward(sd, x, t), "surfz": lambda: O.surfz_forward(sd, x, t, sP, fm),
+                       "edgepos": lambda: O.edgepos_forward(sd, x, t, sP, sZ, fm),
+                       "edgez": lambda: O.edgez_forward(sd, x, t, eP, sP, sZ, em)}[knd]
             if inner_warm:
                 orc.step(fwd(), 500, x, r(*shape))
             t0 = time.perf_counter()
@@ -117,10 +136,11 @@ def cpu_reference_sample(S0, S, E, reps, threads=None, inner_warm=True):
             per[name] = (time.perf_counter() - t0) / reps
             del sd
     sec_per_brep = 750 * per["surfpos@S0"] + 250 * per["surfpos@S"] + 1000 * (per["surfz"] + per["edgepos"] + per["edgez"])
-    desc = ("oracle fp32 (torch CPU, %d threads), batch 1, %d timed (forward + DDPM step) per stage after warm-up; s/step: "
-            % (cores, reps) +
-            ", ".join(f"{k}={v:.3f}" for k, v in per.items()) + "; extrapolated to 750/250 + 3x1000 steps")
-    return 1.0 / sec_per_brep, cores, desc
+    what = ("the reference's own classes (network.py:1066-1393, stock nn.TransformerEncoder path)" if used == "reference"
+            else "oracle port (oracle/denoisers.py)")
+    desc = (f"{what}, fp32 torch CPU, {cores} threads, batch 1, {reps} timed (forward + DDPM step) per stage after warm-up; "
+            "s/step: " + ", ".join(f"{k}={v:.3f}" for k, v in per.items()) + "; extrapolated to 750/250 + 3x1000 steps")
+    return 1.0 / sec_per_brep, cores, desc, used
 
 
 def best_cpu_threads():
@@ -189,16 +209,22 @@ def run_reference(args):
         cpu_reference_sample(S0, S, E, 1, nthr, inner_warm=False)      # never time a cold first pass
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        v, cores, desc = cpu_reference_sample(S0, S, E, 1, nthr, inner_warm=False)
+        v, cores, desc, used = cpu_reference_sample(S0, S, E, 1, nthr, inner_warm=False)
         vals.append(v)
+    port = None
+    if used == "reference":     # the pinned restatement beside it (one pass), so both CPU numbers are on record
+        pv, _, pdesc, _ = cpu_reference_sample(S0, S, E, 1, nthr, inner_warm=True, kind="port")
+        port = {"value": pv, "unit": UNIT, "kind": "port", "sample": pdesc}
     ms = (time.perf_counter() - t0) / max(args.steps, 1) * 1e3
     v = sum(vals) / len(vals)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"abc_cascade S0={S0}->S={S} E={E} L_edge={S * E}, dense masks, 4x1000 DDPM steps",
-                       "note": "reference algorithm on host cores (its CUDA path needs diffusers/OCC, absent offline)"},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+                       "note": "the reference's CPU PyTorch path on the host cores: batch 1, one forward + scheduler step per "
+                               "stage per bench step, extrapolated (one ABC B-rep is ~1 h of CPU); its own sample.py needs "
+                               "diffusers/OCC/CUDA, absent offline"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": used, "sample": desc, "port": port},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -344,8 +370,8 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cores, desc = cpu_reference_sample(S0, S, E, 1, best_cpu_threads())
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+        v, cores, desc, used = cpu_reference_sample(S0, S, E, 1, best_cpu_threads())
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": used, "sample": desc}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

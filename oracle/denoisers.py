@@ -67,10 +67,10 @@ def encoder(sd: SD, x: torch.Tensor, key_padding_mask: Optional[torch.Tensor], p
         q = q.view(B, L, NHEAD, dh).transpose(1, 2)
         k = k.view(B, L, NHEAD, dh).transpose(1, 2)
         v = v.view(B, L, NHEAD, dh).transpose(1, 2)
-        s = (q @ k.transpose(-1, -2)) / math.sqrt(dh)
-        if bias is not None:
-            s = s + bias
-        a = torch.softmax(s, dim=-1) @ v
+        # softmax(q k^T / sqrt(dh) + kpm) v through torch's fused CPU kernel: the same arithmetic without the
+        # (B, 12, L, L) score tensor (768 MB per layer at L = 4000), which is also how the reference's
+        # nn.MultiheadAttention evaluates it -- the materialised form was 6x slower and not representative as a baseline
+        a = F.scaled_dot_product_attention(q, k, v, attn_mask=bias)
         a = a.transpose(1, 2).reshape(B, L, D)
         x = x + _lin(a, sd, p + ".self_attn.out_proj")
         h = _ln(x, sd, p + ".norm2")

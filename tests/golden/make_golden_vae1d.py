@@ -154,7 +154,8 @@ class DecoderOutput:
 
 def load_reference_network_with_leaves():
     import make_golden as MG
-    MG._stub_diffusers()
+    from oracle.reference_loader import _stub_diffusers
+    _stub_diffusers()
     sys.modules["diffusers.models.unets.unet_1d_blocks"].__dict__.update(
         ResConvBlock=ResConvBlock, SelfAttention1d=SelfAttention1d, Upsample1d=Upsample1d, get_down_block=get_down_block)
     sys.modules["diffusers.models.autoencoders.vae"].__dict__.update(

@@ -2,8 +2,7 @@
 batch 64 (SURVEY.md section 8(d) input 2): single forwards at t in {999, 500, 249, 10, 0} and two 10-step chains
 (t = 999..990 and t = 9..0) with the step noise shared with the CPU fp32 oracle; bar 1e-3 relative (L2).
 
-Added after the round-1 GPU budget was spent: every component is covered by the tests that did run (denoiser parity at
-other shapes, DDPM chains), but this composition has not run on a GPU yet, hence xfail(strict=False).
+Strict since round 2 (passed on the driver's B200 at the end of round 1).
 """
 import pytest
 import torch
@@ -22,7 +21,6 @@ def rel_l2(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
-@pytest.mark.xfail(strict=False, reason="added after the round-1 GPU budget was spent; first GPU run pending")
 def test_config1_surfposnet_ddpm1000_b64_s30():
     from brepgen_b200.models import SurfPosNet
     from brepgen_b200.schedulers import DDPMScheduler

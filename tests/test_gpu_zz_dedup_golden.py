@@ -1,8 +1,7 @@
 """GPU: the de-duplication kernels against the outputs of the reference's OWN statements (tests/golden/dedup_golden.npz,
 written by tests/golden/make_golden_dedup.py from sample.py:159-183 and :242-261): packed boxes and masks bit-exact.
 
-Added after the round-1 GPU budget was spent (the kernels are bit-exact against the oracle in the tests that did run, and
-the oracle reproduces these vectors exactly on the CPU): xfail(strict=False) until its first GPU run."""
+Strict since round 2 (passed on the driver's B200 at the end of round 1)."""
 import os
 
 import numpy as np
@@ -14,7 +13,6 @@ GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "dedup_golden.n
 CASES = sorted(k[:-len("_surfPos_in")] for k in GOLD.files if k.endswith("_surfPos_in"))
 
 
-@pytest.mark.xfail(strict=False, reason="added after the round-1 GPU budget was spent; first GPU run pending")
 @pytest.mark.parametrize("case", CASES)
 def test_dedup_kernels_match_reference_statements(case):
     from brepgen_b200.sampler import dedup_edges, dedup_surfaces

@@ -4,8 +4,7 @@ block, sample.py:122-299, executed verbatim around stand-in networks (tests/gold
 tests/golden/make_golden_driver.py).  The same stand-ins (plain torch functions with the reference's forward signatures)
 are plugged into Cascade here, so everything between the network calls is the code under test.
 
-Added after the round-1 GPU budget was spent: not yet run on a GPU, hence xfail(strict=False) -- it cannot turn the suite
-red, an XPASS means it can be made strict.
+Strict since round 2 (passed on the driver's B200 at the end of round 1).
 """
 import os
 import sys
@@ -18,7 +17,6 @@ pytestmark = pytest.mark.gpu
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
 
 
-@pytest.mark.xfail(strict=False, reason="added after the round-1 GPU budget was spent; first GPU run pending")
 @pytest.mark.parametrize("case", ["abc_like", "furniture_like"])
 def test_product_driver_matches_reference_statements(case):
     import make_golden_driver as G

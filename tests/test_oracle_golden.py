@@ -82,3 +82,19 @@ def test_cascade_driver_matches_reference_statements(case):
         got = out[k].numpy()
         assert got.shape == ref.shape, (k, got.shape, ref.shape)
         assert np.allclose(got, ref, rtol=1e-5, atol=1e-6), (k, float(np.abs(got - ref).max()))
+
+
+def test_oracle_matches_reference_at_benchmark_shape():
+    """the restatement against the reference's own EdgeZNet at S = 100, E = 40 (L = 4000), B = 3, ragged face masks plus
+    30 % random edge masks (tests/golden/make_golden_l4000.py): the L > 128, masked path at the benchmark's own shape"""
+    from make_golden_l4000 import CASES, case_inputs_l4000
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "denoisers_l4000_golden.npz"))
+    name = "edgez_ragged_b3"
+    spec = CASES[name]
+    inp, valid = case_inputs_l4000(spec)
+    sd = synth_state_dict(denoiser_spec(spec[0], spec[1]), seed=7)
+    with torch.no_grad():
+        y = O.FORWARDS[spec[0]](sd, *inp.values())
+    ref = torch.from_numpy(gold[name])
+    err = float((y[valid] - ref[valid]).abs().max() / ref[valid].abs().max())
+    assert err < 2e-5, err
