@@ -38,7 +38,9 @@ unsigned long long launch_count();
     if (!(cond)) return ::bg::set_error(::bg::BG_ERR_BAD_ARG, std::string(msg) + " [" #cond "]"); \
   } while (0)
 
-int num_sms();   // of the current device (cached)
+int num_sms();   // of the current device (cached per device)
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device)
+int ensure_dynamic_smem(const void* func, int bytes);
 
 // ---- TMA descriptor creation (driver entry point resolved at run time; no link dependency on libcuda) ----
 // 2-D fp16 row-major [rows][cols] with row pitch ld (elements); box = {box_cols(=64), box_rows}; SWIZZLE_128B.

@@ -1,5 +1,7 @@
 // Error plumbing, device queries and TMA descriptor creation shared by all translation units.
+#include <map>
 #include <mutex>
+#include <utility>
 
 #include "bg_internal.h"
 
@@ -25,17 +27,32 @@ int check_launch(const char* what) {
 }
 unsigned long long launch_count() { return g_launches; }
 
+// Per-DEVICE caches: one process may drive several GPUs (models.py / vae.py switch devices with torch.cuda.device), and both
+// the SM count and cudaFuncAttributeMaxDynamicSharedMemorySize are per device / context.
+static constexpr int MAX_DEV = 64;
+
 int num_sms() {
-  static int cached = 0;
-  if (cached == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-      cached = n;
-    else
-      cached = 148;
+  static int cached[MAX_DEV] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    cached[dev] = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
   }
-  return cached;
+  return cached[dev];
+}
+
+int ensure_dynamic_smem(const void* func, int bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, int> done;   // (kernel, device) -> configured bytes
+  int dev = 0;
+  BG_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = done.find({func, dev});
+  if (it != done.end() && it->second >= bytes) return BG_OK;
+  BG_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done[{func, dev}] = bytes;
+  return BG_OK;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

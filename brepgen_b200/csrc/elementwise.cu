@@ -165,11 +165,16 @@ __global__ void cond_kernel(const float* __restrict__ time_table, const int64_t*
                             const float* __restrict__ class_table, const int64_t* __restrict__ label,
                             float* __restrict__ cond, int B) {
   const int b = blockIdx.x;
-  long long tt = t[n_t == 1 ? 0 : b];
-  tt = tt < 0 ? 0 : (tt > 999 ? 999 : tt);
-  const float* tr = time_table + (size_t)tt * D;
-  const float* cr = class_table ? class_table + (size_t)label[b] * D : nullptr;
-  for (int i = threadIdx.x; i < D; i += blockDim.x) cond[(size_t)b * D + i] = tr[i] + (cr ? cr[i] : 0.f);
+  // A timestep outside the 1000-row table or a class label outside the 11-row embedding is an error in the caller (the
+  // reference's nn.Embedding raises a device assert).  There is no error channel from a stream-ordered kernel, so the
+  // sample's conditioning is poisoned with NaN instead of reading out of bounds: every output of that sample is NaN.
+  const long long tt = t[n_t == 1 ? 0 : b];
+  const long long lb = class_table ? label[b] : 0;
+  const bool bad = tt < 0 || tt > 999 || lb < 0 || lb >= 11;
+  const float* tr = time_table + (size_t)(bad ? 0 : tt) * D;
+  const float* cr = class_table ? class_table + (size_t)(bad ? 0 : lb) * D : nullptr;
+  const float poison = bad ? __int_as_float(0x7fc00000) : 0.f;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) cond[(size_t)b * D + i] = tr[i] + (cr ? cr[i] : 0.f) + poison;
 }
 
 __global__ void sincos_table_kernel(float* __restrict__ out, int n) {
@@ -221,11 +226,7 @@ int launch_ln_silu_head(cudaStream_t st, const float* x, int ldx, const float* g
                         const float* bias, float* out, int d_out, int rows) {
   BG_REQUIRE(rows > 0 && d_out > 0 && d_out <= 64 && ldx % 4 == 0, "ln_silu_head: bad shape");
   const int smem = d_out * D * 4;
-  static bool configured = false;
-  if (!configured) {
-    BG_CUDA(cudaFuncSetAttribute(ln_silu_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * D * 4));
-    configured = true;
-  }
+  BG_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&ln_silu_head_kernel), 64 * D * 4));
   const int want = (rows + 7) / 8;
   const int cap = num_sms() * 2;
   ln_silu_head_kernel<<<want < cap ? want : cap, 256, smem, st>>>(x, ldx, g, b, W, bias, out, d_out, rows);

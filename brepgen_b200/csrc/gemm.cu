@@ -162,11 +162,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 template <int BN>
 int launch_bn(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p) {
   using C = Cfg<BN>;
-  static bool configured = false;
-  if (!configured) {
-    BG_CUDA(cudaFuncSetAttribute(gemm_f16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    configured = true;
-  }
+  BG_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&gemm_f16_kernel<BN>), C::SMEM_BYTES));
   const int num_tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
   gemm_f16_kernel<BN><<<grid, 384, C::SMEM_BYTES, st>>>(tmA, tmB, p);

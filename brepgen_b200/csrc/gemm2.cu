@@ -1,4 +1,4 @@
-// 2-CTA (cta_group::2) variant of the tcgen05 GEMM of gemm.cu:  out[M,N] = epi( A[M,K] * W[N,K]^T ).
+// 2-CTA (cta_group::2) tcgen05 GEMM:  out[M,N] = epi( A[M,K] * W[N,K]^T ), default for N % 256 == 0 (gemm.cu: N = 128 tiles).
 //
 // A CTA pair (thread-block cluster of 2, same TPC) computes one 256 x 256 tile: each CTA owns 128 rows of M (its own A
 // tile and its own 128 x 256 fp32 accumulator in TMEM) and loads only HALF of the 256 weight rows; the leader CTA's single
@@ -11,8 +11,16 @@
 //   warp 1 (leader)   : MMA issuer; tcgen05.commit ... multicast::cluster arrives on the empty / tmem-full barriers of
 //                       BOTH CTAs
 //   warp 2 (both)     : TMEM allocator (tcgen05.alloc.cta_group::2, 512 columns: accumulator double buffer)
-//   warps 4-11 (both) : epilogue (gemm_epilogue.cuh); all 512 epilogue threads of the pair arrive on the leader's
-//                       tmem-empty barrier (the peer through a cluster-mapped address)
+//   warps 4-11 (both) : epilogue; all 512 epilogue threads of the pair arrive on the leader's tmem-empty barrier (the
+//                       peer through a cluster-mapped address)
+//
+// Two epilogues (template parameter RES):
+//   RES = 0  gemm_epilogue.cuh: fp16 outputs written directly, fp32 outputs transposed through shared memory; 6-stage ring.
+//   RES = 1  the in-place fp32 residual GEMMs  X += A W^T + b  (out-proj, FFN2), which are HBM-bound by construction
+//            (256 KB of residual in + result out per 128 x 256 tile against 2048 tensor cycles): each epilogue warp
+//            TMA-loads the residual 32 x 32 sub-tile into a swizzled staging buffer one chunk ahead, adds accumulator + bias
+//            there and TMA-stores it -- deep asynchronous queues instead of per-warp load / store bursts.  Measured at
+//            M = 256 000 (B = 64): out-proj 665 -> 580 us (4.07 TB/s), FFN2 571 -> 423 us (4.96 TB/s).  4-stage ring.
 #include <stdlib.h>
 
 #include "bg_internal.h"
@@ -26,13 +34,33 @@ namespace {
 constexpr int BM_CTA = 128;     // rows per CTA; the pair covers 256
 constexpr int BN = 256;
 constexpr int BK = 64;
-constexpr int STAGES = 6;
+constexpr int NSTAGES = 6;
 constexpr int A_BYTES = BM_CTA * BK * 2;
 constexpr int B_BYTES = (BN / 2) * BK * 2;
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;            // 32 KB per CTA
 constexpr int BAR_BYTES = 256;
 constexpr int XPOSE_BYTES = 8 * 32 * GEMM_XPOSE_PITCH * 4;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + XPOSE_BYTES + 1024;
+constexpr int SMEM_BYTES = NSTAGES * STAGE_BYTES + BAR_BYTES + XPOSE_BYTES + 1024;
+// RES == 1 (TMA-staged residual epilogue): 4-stage ring, 1 KB of barriers, then 8 warps x 3 buffers of 32 rows x 128 B
+constexpr int X_STAGES = 4;
+constexpr int X_BUF_BYTES = 32 * 128;
+constexpr int X_BUFS = 3;
+constexpr int X_OFF_BAR = X_STAGES * STAGE_BYTES;
+constexpr int X_OFF_STG = X_OFF_BAR + 1024;
+constexpr int X_SMEM_BYTES = X_OFF_STG + 8 * X_BUFS * X_BUF_BYTES + 1024;
+static_assert(X_SMEM_BYTES <= 232448, "TMA-staged epilogue does not fit in shared memory");
+
+// extra kernel parameter of the RES == 1 variant only
+template <int RES> struct EpiMaps {};
+template <> struct EpiMaps<1> { CUtensorMap x; };     // fp32 [M][ldo] residual / output matrix, box 32 x 32, SWIZZLE_128B
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 constexpr int TMEM_COLS = 512;
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;               // shared::cluster address of the same offset in the even (leader) CTA
 
@@ -68,8 +96,11 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 
+template <int RES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
-gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p,
+                 const __grid_constant__ EpiMaps<RES> em) {
+  constexpr int STAGES = RES ? X_STAGES : NSTAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -86,6 +117,7 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if constexpr (RES == 1) tma_prefetch_desc(&em.x);
   }
   if (warp == 1 && elect_one()) {
     for (int i = 0; i < STAGES; ++i) {
@@ -95,6 +127,10 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], 512);      // leader: 256 epilogue threads of each CTA
+    }
+    if constexpr (RES == 1) {           // residual-load barriers: 3 per epilogue warp, one arrive.expect_tx each
+      uint64_t* xbar = reinterpret_cast<uint64_t*>(smem + X_OFF_BAR + 256);
+      for (int i = 0; i < 8 * X_BUFS; ++i) mbar_init(&xbar[i], 1);
     }
     fence_barrier_init();
   }
@@ -167,18 +203,74 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     float* xp = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + BAR_BYTES) + (warp - 4) * 32 * GEMM_XPOSE_PITCH;
     int acc = 0;
     uint32_t accphase = 0;
+    // RES == 1: this warp's three 4 KB staging buffers (32 rows x 128 B, SWIZZLE_128B), their load barriers and the
+    // running chunk counter q (buffer q % 3, barrier phase (q / 3) & 1)
+    uint8_t* xstg = smem + X_OFF_STG + (warp - 4) * X_BUFS * X_BUF_BYTES;
+    uint64_t* xbar = reinterpret_cast<uint64_t*>(smem + X_OFF_BAR + 256) + (warp - 4) * X_BUFS;
+    uint32_t q = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
       const int row0 = m_blk * 2 * BM_CTA + (int)rank * BM_CTA + ew * 32;
       const int colbase = n_blk * BN + half * (BN / 2);
-      mbar_wait(&tfull[acc], accphase);
-      tc_fence_after();
-      gemm_epilogue_tile<CHUNKS>(p, tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN + half * (BN / 2), row0, colbase, xp, lane);
+      if constexpr (RES == 1) {
+        // ---- TMA-staged residual epilogue: out = resid (in place) + acc + bias, fp32 ----
+        // residual chunk c+1 is loaded (TMA, swizzled rows) while chunk c is combined in shared memory and stored (TMA):
+        // the memory system sees deep asynchronous queues instead of per-warp load / store bursts
+        auto issue_load = [&](uint32_t qq, int c) {      // lane 0 only
+          bulk_wait_read<1>();                           // the store that last read buffer qq % 3 (two chunks ago) is done with it
+          const uint32_t b = qq % X_BUFS;
+          mbar_arrive_expect_tx(&xbar[b], X_BUF_BYTES);
+          tma_load_2d(xstg + b * X_BUF_BYTES, &em.x, &xbar[b], colbase + c * 32, row0);
+        };
+        if (lane == 0) issue_load(q, 0);                 // overlaps the wait for the accumulator
+        mbar_wait(&tfull[acc], accphase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN + half * (BN / 2);
+#pragma unroll 1
+        for (int c = 0; c < CHUNKS; ++c) {
+          if (c + 1 < CHUNKS && lane == 0) issue_load(q + 1, c + 1);
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(taddr + c * 32, r);
+          const uint32_t b = q % X_BUFS;
+          mbar_wait(&xbar[b], (q / X_BUFS) & 1);         // residual chunk c is in shared memory
+          tmem_ld_wait();
+          const int col0 = colbase + c * 32;
+          const uint32_t rowaddr = smem_u32(xstg + b * X_BUF_BYTES) + lane * 128;   // this thread's accumulator row
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t a = rowaddr + ((j ^ (lane & 7)) << 4);                   // 16-byte chunk j of the row, 128B swizzle
+            float4 v;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+            float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias) bb = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
+            v.x += __uint_as_float(r[4 * j]) + bb.x;
+            v.y += __uint_as_float(r[4 * j + 1]) + bb.y;
+            v.z += __uint_as_float(r[4 * j + 2]) + bb.z;
+            v.w += __uint_as_float(r[4 * j + 3]) + bb.w;
+            if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+          }
+          fence_proxy_async_smem();                      // generic-proxy writes -> visible to the TMA store
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&em.x, xstg + b * X_BUF_BYTES, col0, row0);    // rows >= M are clipped by the tensor map
+            bulk_commit();
+          }
+          ++q;
+        }
+      } else {
+        mbar_wait(&tfull[acc], accphase);
+        tc_fence_after();
+        gemm_epilogue_tile<CHUNKS>(p, tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN + half * (BN / 2), row0, colbase, xp, lane);
+      }
       tc_fence_before();
       if (leader) mbar_arrive(&tempty[acc]);
       else mbar_arrive_cluster(&tempty[acc], 0);
       acc ^= 1;
       if (acc == 0) accphase ^= 1;
+    }
+    if constexpr (RES == 1) {
+      if (lane == 0) bulk_wait_all();   // every TMA store of this thread has completed before the CTA may exit
     }
   }
 
@@ -189,25 +281,20 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 }  // namespace
 
-int launch_gemm2x_f16(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int variant);   // gemm2x.cu
-
-// N % 256 == 0 path of launch_gemm_f16 when BG_GEMM_2CTA != 0
+// N % 256 == 0 path of launch_gemm_f16
 int launch_gemm2_f16(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p) {
-  static int variant = -1;              // BG_GEMM_PF = 1 | 2: experimental epilogues (gemm2x.cu); unset / 0: this kernel
-  if (variant < 0) {
-    const char* e = getenv("BG_GEMM_PF");
-    variant = e ? atoi(e) : 0;
-  }
-  if (variant == 1 || variant == 2) return launch_gemm2x_f16(st, tmA, tmB, p, variant);
-  static bool configured = false;
-  if (!configured) {
-    BG_CUDA(cudaFuncSetAttribute(gemm2_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    configured = true;
-  }
   const int num_tiles = ((p.M + 255) / 256) * (p.N / BN);
   const int max_clusters = num_sms() / 2;
   const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
-  gemm2_f16_kernel<<<2 * clusters, 384, SMEM_BYTES, st>>>(tmA, tmB, p);
+  if (!p.out_f16 && p.resid != nullptr && p.resid == p.out && p.ldr == p.ldo && p.rowvec == nullptr) {
+    BG_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&gemm2_f16_kernel<1>), X_SMEM_BYTES));
+    EpiMaps<1> em;
+    BG_TRY(make_tmap_2d_f32(&em.x, p.out, (uint64_t)p.M, (uint64_t)p.N, (uint64_t)p.ldo, 32, 32));
+    gemm2_f16_kernel<1><<<2 * clusters, 384, X_SMEM_BYTES, st>>>(tmA, tmB, p, em);
+  } else {
+    BG_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&gemm2_f16_kernel<0>), SMEM_BYTES));
+    gemm2_f16_kernel<0><<<2 * clusters, 384, SMEM_BYTES, st>>>(tmA, tmB, p, EpiMaps<0>{});
+  }
   return check_launch("gemm2_f16_kernel launch");
 }
 

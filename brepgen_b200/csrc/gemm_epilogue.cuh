@@ -113,53 +113,4 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
       }
 }
 
-
-// Variant with the residual loads software-pipelined one 32-column chunk ahead (opt-in: BG_GEMM_PF=1, gemm2.cu).
-// The out-proj / FFN2 GEMMs add into the fp32 residual stream and are HBM-bound (256 KB of residual + result per
-// 128 x 256 tile against 2048 tensor cycles); in the plain form every warp alternates "32 loads in flight" and "transpose
-// + 32 stores", so the memory pipe sees bursts.  Here the loads of chunk c+1 are issued before chunk c is transposed and
-// stored.  fp32 output with residual only; every other case falls through to gemm_epilogue_tile.
-template <int CHUNKS>
-__device__ __forceinline__ void gemm_epilogue_tile_pf(const GemmParams& p, uint32_t taddr, int row0, int colbase, float* xp,
-                                                      int lane) {
-  if (p.out_f16 || !p.resid || p.rowvec) {
-    gemm_epilogue_tile<CHUNKS>(p, taddr, row0, colbase, xp, lane);
-    return;
-  }
-  constexpr int PITCH = GEMM_XPOSE_PITCH;
-  float* ob = reinterpret_cast<float*>(p.out);
-  float cur[32], nxt[32];
-  auto load_resid = [&](int c, float (&dst)[32]) {
-    const int col = colbase + c * 32 + lane;
-#pragma unroll
-    for (int rr = 0; rr < 32; ++rr) {
-      const int row = row0 + rr;
-      dst[rr] = row < p.M ? p.resid[(size_t)row * p.ldr + col] : 0.f;
-    }
-  };
-  load_resid(0, nxt);
-#pragma unroll
-  for (int c = 0; c < CHUNKS; ++c) {
-    const int col = colbase + c * 32 + lane;
-    const float bias = p.bias ? __ldg(p.bias + col) : 0.f;
-#pragma unroll
-    for (int rr = 0; rr < 32; ++rr) cur[rr] = nxt[rr];
-    if (c + 1 < CHUNKS) load_resid(c + 1, nxt);          // in flight while this chunk is transposed and stored
-    uint32_t r[32];
-    tmem_ld_32x32b_x32(taddr + c * 32, r);
-    tmem_ld_wait();
-    __syncwarp();                                        // previous chunk's reads of xp are done
-#pragma unroll
-    for (int i = 0; i < 32; ++i) xp[lane * PITCH + i] = __uint_as_float(r[i]);
-    __syncwarp();
-#pragma unroll
-    for (int rr = 0; rr < 32; ++rr) {
-      float v = xp[rr * PITCH + lane] + bias + cur[rr];
-      if (p.relu) v = fmaxf(v, 0.f);
-      const int row = row0 + rr;
-      if (row < p.M) ob[(size_t)row * p.ldo + col] = v;
-    }
-  }
-}
-
 }  // namespace bg

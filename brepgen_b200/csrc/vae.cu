@@ -670,11 +670,7 @@ int im2col1d(const Ctx& c, const __half* in, int L, int C, int ks, int kpad) {
 int attention(const Ctx& c, int T, int Hh, int dh, float scale) {
   const int C = Hh * dh;
   const size_t smem = (size_t)(3 * T * C + Hh * T * T) * 4;
-  static bool configured = false;
-  if (!configured) {
-    BG_CUDA(cudaFuncSetAttribute(small_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-    configured = true;
-  }
+  BG_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&small_attention_kernel), 112 * 1024));
   small_attention_kernel<<<(unsigned)c.N, 256, smem, c.st>>>(c.w.Q, c.w.Q + c.N * (size_t)T * 3 * C, T, Hh, dh, scale);   // out: [N*T][2C]
   return check_launch("small_attention_kernel launch");
 }

@@ -119,7 +119,10 @@ class Cascade:
             k += 1
         return x
 
-    def _stage(self, cfg, x, fwd, label2, gen, hybrid_ddpm_tail: bool, on_step=None, noise_fn=None):
+    _STAGE_ID = {"surfPos": 0, "surfZ": 1, "edgePos": 2, "edgeZV": 3}
+
+    def _stage(self, cfg, x, fwd, label2, gen, hybrid_ddpm_tail: bool, on_step=None, noise_fn=None, name="surfPos"):
+        self.ddpm.set_noise_seed(*getattr(self, "_noise_key", (int(cfg.seed), 0)), self._STAGE_ID[name])
         if cfg.schedule == "ddpm":
             self.ddpm.set_timesteps(cfg.ddpm_steps)
             return self._loop(cfg, self.ddpm, self.ddpm.timesteps, x, fwd, label2, gen, on_step, noise_fn)
@@ -138,8 +141,16 @@ class Cascade:
     @torch.no_grad()
     def run(self, cfg: CascadeConfig, init_noise: Optional[Dict[str, torch.Tensor]] = None, step_noise=None):
         """step_noise(stage_name, k, shape) -> tensor: explicit DDPM step noise (parity runs); default = in-kernel Philox
-        seeded from torch.cuda.initial_seed()."""
+        keyed by (cfg.seed, rank, stage): reproducible from cfg.seed, independent across ranks and stages."""
         dev = self.device
+        rank = 0
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                rank = dist.get_rank()
+        except Exception:
+            pass
+        self._noise_key = (int(cfg.seed), rank)
         nf = (lambda name: (lambda k, shape: step_noise(name, k, shape))) if step_noise is not None else (lambda name: None)
         gen = None
         B, S0, E = cfg.batch_size, cfg.num_surfaces, cfg.num_edges
@@ -168,7 +179,7 @@ class Cascade:
 
         surfPos = noise("surfPos", (B, S0, 6))
         surfPos = self._stage(cfg, surfPos, lambda x, t: self.m["surfpos"](x, t, label2), label2, gen, True,
-                              on_step=late_increase, noise_fn=nf("surfPos"))
+                              on_step=late_increase, noise_fn=nf("surfPos"), name="surfPos")
         if not late["done"]:
             surfPos = surfPos.repeat(1, 2, 1)
 
@@ -182,13 +193,13 @@ class Cascade:
         # STEP 1-3 surface latents (sample.py:189-202)
         surfZ = noise("surfZ", (B, S, 48))
         surfZ = self._stage(cfg, surfZ, lambda x, t: self.m["surfz"](x, t, sP, sM, label2), label2, gen, False,
-                            noise_fn=nf("surfZ"))
+                            noise_fn=nf("surfZ"), name="surfZ")
         sZ = rep2(surfZ)
 
         # STEP 2-1 edge positions (sample.py:208-236)
         edgePos = noise("edgePos", (B, S, E, 6))
         edgePos = self._stage(cfg, edgePos, lambda x, t: self.m["edgepos"](x, t, sP, sZ, sM, label2), label2, gen, True,
-                              noise_fn=nf("edgePos"))
+                              noise_fn=nf("edgePos"), name="edgePos")
 
         # STEP 2-2 duplicate edges per face (sample.py:242-261)
         if cfg.dense_masks:
@@ -200,7 +211,7 @@ class Cascade:
         # STEP 2-3 edge latents + vertices (sample.py:267-286)
         edgeZV = noise("edgeZV", (B, S, E, 18))
         edgeZV = self._stage(cfg, edgeZV, lambda x, t: self.m["edgez"](x, t, eP, sP, sZ, eM, label2), label2, gen, False,
-                             noise_fn=nf("edgeZV"))
+                             noise_fn=nf("edgeZV"), name="edgeZV")
         edgeZV = edgeZV.masked_fill(edgeM.unsqueeze(-1), 0.0)
         edge_z, edgeV = edgeZV[..., :12], edgeZV[..., 12:]
 

@@ -37,6 +37,17 @@ def _betas(num_train_timesteps, beta_start, beta_end, beta_schedule):
     raise NotImplementedError(f"beta_schedule={beta_schedule!r} (the reference uses 'linear', sample.py:103,111)")
 
 
+def mix_seed(*parts: int) -> int:
+    """64-bit key from a tuple of integers (splitmix64 finaliser per part): distinct tuples -> independent Philox keys"""
+    h = 0x9E3779B97F4A7C15
+    for p in parts:
+        z = (h ^ (int(p) & 0xFFFFFFFFFFFFFFFF)) + 0x9E3779B97F4A7C15 & 0xFFFFFFFFFFFFFFFF
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+        h = z ^ (z >> 31)
+    return h
+
+
 def _as_int(t) -> int:
     return int(t.item()) if torch.is_tensor(t) else int(t)
 
@@ -61,8 +72,17 @@ class DDPMScheduler:
         self.alphas_cumprod = torch.cumprod(self.alphas, dim=0)
         self.one = torch.tensor(1.0)
         self.init_noise_sigma = 1.0
+        self._philox_seed = None       # None: derived from torch.initial_seed() at first use (follows torch.manual_seed)
         self._philox_offset = 0
         self.set_timesteps(num_train_timesteps)
+
+    def set_noise_seed(self, seed: int, *stream: int):
+        """Key of the in-kernel Philox stream that `step` draws its noise from when neither `noise` nor `generator` is
+        given: a 64-bit mix of `seed` and any further integers (rank, stage, ...).  Resets the stream offset, so a run is
+        reproducible from the seed alone and different (seed, rank, stage) tuples give independent streams
+        (per-rank independent RNG streams)."""
+        self._philox_seed = mix_seed(seed, *stream)
+        self._philox_offset = 0
 
     def set_timesteps(self, num_inference_steps: int, device=None):
         n_train = self.config.num_train_timesteps
@@ -112,13 +132,18 @@ class DDPMScheduler:
         eps = model_output.float().contiguous()
         eps_u = None if model_output_uncond is None else model_output_uncond.float().contiguous()
         if noise is None and generator is not None and sigma != 0.0:
-            noise = torch.randn(x.shape, generator=generator, device=x.device, dtype=torch.float32)
+            # diffusers' randn_tensor: a CPU generator samples on the CPU and the result is moved to the device
+            gdev = generator.device if hasattr(generator, "device") else torch.device("cpu")
+            noise = torch.randn(x.shape, generator=generator, device=x.device if gdev.type == "cuda" else "cpu",
+                                dtype=torch.float32)
         if noise is not None:
             noise = noise.to(device=x.device, dtype=torch.float32).contiguous()
         n = x.numel()
         seed, offset = 0, 0
         if noise is None and sigma != 0.0:
-            seed = torch.cuda.initial_seed() & 0xFFFFFFFFFFFFFFFF
+            if self._philox_seed is None:
+                self._philox_seed = mix_seed(torch.initial_seed())
+            seed = self._philox_seed
             offset = self._philox_offset
             self._philox_offset += (n + 3) // 4
         dst = torch.empty_like(x) if out is None else out

@@ -155,3 +155,33 @@ def test_hybrid_schedule_runs_and_counts_steps():
     assert counts == {"surfpos": 408, "surfz": 209, "edgepos": 408, "edgez": 209}
     assert out["surfPos"].shape == (1, 6, 6) and out["edgeV"].shape == (1, 6, 2, 6)
     assert all(torch.isfinite(v.float()).all() for v in out.values())
+
+
+def test_step_noise_is_reproducible_and_rank_dependent():
+    """in-kernel Philox step noise: same (seed, rank, stage) -> identical x_{t-1}; another rank or stage -> different noise;
+    a CPU generator is honoured like diffusers' randn_tensor does (sampled on the CPU, moved to the device)"""
+    from brepgen_b200.schedulers import DDPMScheduler
+    g = torch.Generator().manual_seed(3)
+    x, eps = torch.randn(2, 30, 6, generator=g).cuda(), torch.randn(2, 30, 6, generator=g).cuda()
+
+    def run(*key):
+        s = DDPMScheduler(clip_sample=True, clip_sample_range=3)
+        s.set_noise_seed(*key)
+        y = s.step(eps, 500, x).prev_sample
+        return torch.stack([y, s.step(eps, 499, y).prev_sample])
+
+    a, b, c, d = run(11, 0, 2), run(11, 0, 2), run(11, 1, 2), run(11, 0, 3)
+    assert torch.equal(a, b)
+    assert not torch.allclose(a, c) and not torch.allclose(a, d) and not torch.allclose(c, d)
+    # the two consecutive steps of one run draw different noise (the offset advances)
+    s = DDPMScheduler(clip_sample=True, clip_sample_range=3)
+    s.set_noise_seed(1)
+    zero = torch.zeros_like(x)
+    n1 = s.step(zero, 500, zero).prev_sample
+    n2 = s.step(zero, 500, zero).prev_sample
+    assert not torch.allclose(n1, n2) and abs(float(n1.std() / n2.std()) - 1) < 0.2
+    cg = torch.Generator().manual_seed(9)
+    y1 = DDPMScheduler().step(eps, 500, x, generator=cg).prev_sample
+    cg.manual_seed(9)
+    y2 = DDPMScheduler().step(eps, 500, x, generator=cg).prev_sample
+    assert torch.equal(y1, y2)
