@@ -50,6 +50,9 @@ def parse():
     ap.add_argument("--masks", default="dense", choices=["dense", "flow"],
                     help="dense = every slot valid, the metric's dense-FLOP mode; flow = run both dedups (sample.py:159-183,242-261) "
                          "and mask what they remove (fully padded key blocks are then skipped)")
+    ap.add_argument("--workload", default="cascade", choices=["cascade", "surfpos"],
+                    help="cascade = the metric's workload (BASELINE configs[2]); surfpos = BASELINE configs[1]: SurfPosNet, "
+                         "1000-step DDPM, 30 face tokens, batch 64 (first stage only), eager loop vs CUDA-graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -229,10 +232,51 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_surfpos(args):
+    """BASELINE configs[1]: SurfPosNet 1000-step DDPM, 30 face-bbox tokens, batch 64, one GPU.  1 920 tokens per forward: the
+    GPU needs ~0.3 ms per step, ~105 launches from Python need more -- the loop is captured in a CUDA graph
+    (sampler.Cascade._loop_graph) and replayed.  Prints one JSON line (not the headline metric: first stage only)."""
+    from brepgen_b200 import _ffi
+    from brepgen_b200.models import NETS
+    from brepgen_b200.sampler import Cascade, CascadeConfig
+    from brepgen_b200.spec import denoiser_spec
+    from brepgen_b200.synth import synth_state_dict
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    B, S, T = (args.batch if args.batch != 256 else 64), 30, 1000
+    m = NETS["surfpos"](False)
+    m.load_state_dict(synth_state_dict(denoiser_spec("surfpos", False), seed=1))
+    casc = Cascade({"surfpos": m.to(dev).eval()}, device=dev)
+    x = torch.randn(B, S, 6, generator=torch.Generator().manual_seed(0)).to(dev)
+    fwd = lambda xi, t: casc.m["surfpos"](xi, t, None)
+    casc.ddpm.set_timesteps(T)
+    res = {}
+    for mode in ("off", "on"):
+        cfg = CascadeConfig(batch_size=B, schedule="ddpm", graph=mode)
+        with torch.no_grad():
+            casc._loop(cfg, casc.ddpm, casc.ddpm.timesteps[:50], x.clone(), fwd, None, None)      # warm-up
+            torch.cuda.synchronize()
+            l0 = _ffi.lib().bg_launch_count()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            casc._loop(cfg, casc.ddpm, casc.ddpm.timesteps, x.clone(), fwd, None, None)
+            e1.record()
+            torch.cuda.synchronize()
+        res[mode] = {"ms_per_1000_steps": e0.elapsed_time(e1), "value": B / (e0.elapsed_time(e1) / 1e3),
+                     "host_launch_calls": int(_ffi.lib().bg_launch_count() - l0)}
+    print(json.dumps({"metric": "B-reps/sec (SurfPosNet 1000-step DDPM stage, BASELINE configs[1])", "value": res["on"]["value"],
+                      "unit": UNIT, "n_gpus": 1, "higher_is_better": True, "data": "synthetic",
+                      "config": {"workload": f"surfpos B={B} S={S} T={T}", "graph": res["on"], "eager": res["off"],
+                                 "graph_over_eager": res["on"]["value"] / res["off"]["value"],
+                                 "note": "graph time includes warm-up step, capture and 1000 replays"}}))
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "surfpos":
+        return run_surfpos(args)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

@@ -40,10 +40,19 @@ SIGNATURES = {
     "bg_vae_decode_hw": (i32, [vp, vp, i32, i32, vp, vp, sz, vp]),
     "bg_vae_encode": (i32, [vp, vp, i32, i32, vp, vp, sz, vp]),
     "bg_ddpm_step": (i32, [vp, vp, f32, vp, vp, vp, u64, u64, i64, f32, f32, f32, f32, f32, f32, vp]),
+    "bg_ddpm_step_tab": (i32, [vp, vp, f32, vp, vp, u64, u64, u64, i64, vp, vp, f32, vp]),
+    "bg_step_advance": (i32, [vp, i32, vp, vp, vp]),
     "bg_pndm_step": (i32, [vp, vp, i64, f32, f32, vp, f32, vp, f32, vp, f32, vp, f32, vp]),
     "bg_axpby": (i32, [vp, f32, vp, f32, vp, i64, vp]),
     "bg_dedup_surfaces": (i32, [vp, i32, i32, f32, vp, vp, vp]),
     "bg_dedup_edges": (i32, [vp, vp, i32, i32, i32, f32, vp, vp]),
+    "bg_edge_endpoints": (i32, [vp, vp, f32, i64, vp, vp]),
+    "bg_nn_exclude": (i32, [vp, vp, vp, i32, vp, vp]),
+    "bg_pairs_within": (i32, [vp, i32, f32, vp, vp]),
+    "bg_edge_pair_match": (i32, [vp, vp, i32, i32, f32, vp, vp]),
+    "bg_edge_fit": (i32, [vp, vp, i32, vp, vp]),
+    "bg_surf_init": (i32, [vp, vp, vp, vp, vp, i32, vp, vp]),
+    "bg_surf_offset_opt": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, f32, f32, f32, f32, f32, vp, vp, vp]),
     "bg_op_gemm_f16": (i32, [vp, i32, vp, i32, i32, i32, i32, vp, i32, i32, i32, vp, vp, i32, vp, i32, i32, vp]),
     "bg_op_attention": (i32, [vp, vp, i32, i32, vp, i32, vp, vp]),
     "bg_op_layernorm_f16": (i32, [vp, i32, vp, vp, vp, i32, i32, i32, vp]),

@@ -70,6 +70,56 @@ __global__ void __launch_bounds__(256) ddpm_step_kernel(const DdpmP p) {
   }
 }
 
+// Table-driven form for CUDA-graph replay: nothing step-specific is a kernel argument.  The coefficients of step k live in
+// coef[k][0..4] = (sqrt(1-abar_t), sqrt(abar_t), c_x0, c_x, sigma), k = *step is a device counter that bg_step_advance moves
+// on once per step, and the Philox counter starts at offset0 + k * offset_stride.
+struct DdpmTabP {
+  const float *eps_c, *eps_u, *x;
+  float* out;
+  long long n;
+  float w, clip;
+  const float* coef;
+  const int* step;
+  unsigned long long seed, offset0, offset_stride;
+};
+__global__ void __launch_bounds__(256) ddpm_step_tab_kernel(const DdpmTabP p) {
+  const int k = *p.step;
+  const float* cf = p.coef + 5 * (long long)k;
+  const float sb = cf[0], sa = cf[1], c_x0 = cf[2], c_x = cf[3], sigma = cf[4];
+  const unsigned long long offset = p.offset0 + (unsigned long long)k * p.offset_stride;
+  const long long n4 = (p.n + 3) / 4;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n4; g += (long long)gridDim.x * blockDim.x) {
+    float z[4] = {0.f, 0.f, 0.f, 0.f};
+    if (sigma != 0.f) {
+      uint32_t r[4];
+      const unsigned long long ctr = offset + (unsigned long long)g;
+      philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u, (uint32_t)p.seed, (uint32_t)(p.seed >> 32), r);
+      box_muller(r[0], r[1], z[0], z[1]);
+      box_muller(r[2], r[3], z[2], z[3]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long i = g * 4 + j;
+      if (i >= p.n) break;
+      float e = p.eps_c[i];
+      if (p.eps_u) e = e * (1.f + p.w) - p.eps_u[i] * p.w;
+      const float xv = p.x[i];
+      float x0 = (xv - sb * e) / sa;
+      if (p.clip > 0.f) x0 = fminf(fmaxf(x0, -p.clip), p.clip);
+      float o = c_x0 * x0 + c_x * xv;
+      if (sigma != 0.f) o += sigma * z[j];
+      p.out[i] = o;
+    }
+  }
+}
+// one thread: k = ++(*step);  *t_cur = ts[k]   (the denoiser reads its timestep from t_cur, the step kernel reads k)
+__global__ void step_advance_kernel(const long long* __restrict__ ts, int n, int* __restrict__ step, long long* __restrict__ t_cur) {
+  int k = *step + 1;
+  if (k >= n) k = n - 1;
+  *step = k;
+  *t_cur = ts[k];
+}
+
 struct PndmP {
   const float* x;
   float* out;
@@ -118,6 +168,24 @@ int bg_ddpm_step(const float* eps_cond, const float* eps_uncond, float cfg_w, co
   p.seed = seed; p.offset = offset;
   ddpm_step_kernel<<<grid_for((n + 3) / 4), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   return check_launch("ddpm_step_kernel launch");
+}
+
+int bg_ddpm_step_tab(const float* eps_cond, const float* eps_uncond, float cfg_w, const float* x, float* out, uint64_t seed,
+                     uint64_t offset0, uint64_t offset_stride, int64_t n, const float* coef_table, const int32_t* step,
+                     float clip, void* stream) {
+  BG_REQUIRE(eps_cond && x && out && n > 0 && coef_table && step, "ddpm_step_tab: bad arguments");
+  DdpmTabP p;
+  p.eps_c = eps_cond; p.eps_u = eps_uncond; p.x = x; p.out = out; p.n = n; p.w = cfg_w; p.clip = clip;
+  p.coef = coef_table; p.step = step; p.seed = seed; p.offset0 = offset0; p.offset_stride = offset_stride;
+  ddpm_step_tab_kernel<<<grid_for((n + 3) / 4), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  return check_launch("ddpm_step_tab_kernel launch");
+}
+
+int bg_step_advance(const int64_t* timesteps, int n_steps, int32_t* step, int64_t* t_cur, void* stream) {
+  BG_REQUIRE(timesteps && n_steps > 0 && step && t_cur, "step_advance: bad arguments");
+  step_advance_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const long long*>(timesteps), n_steps,
+                                                                           step, reinterpret_cast<long long*>(t_cur));
+  return check_launch("step_advance_kernel launch");
 }
 
 int bg_pndm_step(const float* x, float* out, int64_t n, float c_sample, float c_eps, const float* e0, float w0,

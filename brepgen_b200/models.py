@@ -71,11 +71,39 @@ class _Denoiser(nn.Module):
         self.precision = int(os.environ.get("BREPGEN_B200_PRECISION", "1"))
         self._handle = None
         self._packed_sig = None
+        self._dirty = True           # parameters may have changed since the last pack (set by load_state_dict / .to() / ...)
         self._ws: Dict[tuple, torch.Tensor] = {}
 
     # ---------------------------------------------------------------- native handle management
     def _signature(self):
         return (self.precision,) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    # The packed device copy is rebuilt when the parameters change.  Walking ~190 parameters on every forward (1600+ forwards
+    # per cascade) is pure host overhead on the latency-critical small-batch path, so the walk only happens after an event
+    # that can change them: load_state_dict, any _apply (.to / .cuda / .float ...), or a changed `precision`.  Code that
+    # writes into parameters in place some other way calls `mark_dirty()`.
+    def mark_dirty(self):
+        self._dirty = True
+
+    def _apply(self, fn, *a, **k):
+        self._dirty = True
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._dirty = True
+        return super().load_state_dict(*a, **k)
+
+    def __deepcopy__(self, memo):
+        import copy
+        new = type(self)(self.use_cf)
+        new.load_state_dict(copy.deepcopy(self.state_dict(), memo))
+        new.precision = self.precision
+        return new
+
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        d["_handle"], d["_packed_sig"], d["_dirty"], d["_ws"] = None, None, True, {}
+        return d
 
     def _release(self):
         if self._handle is not None:
@@ -89,8 +117,11 @@ class _Denoiser(nn.Module):
             pass
 
     def _ensure_packed(self, device):
+        if self._handle is not None and not self._dirty and self._packed_sig[0] == self.precision:
+            return
         sig = self._signature()
         if self._handle is not None and sig == self._packed_sig:
+            self._dirty = False
             return
         self._release()
         sd = {k: v.detach() for k, v in self.state_dict().items()}
@@ -107,7 +138,7 @@ class _Denoiser(nn.Module):
         _ffi.check(_ffi.lib().bg_denoiser_create(_KIND_ID[self.kind], int(self.use_cf), int(self.precision), arr, len(sd),
                                                 sincos.data_ptr(), st, C.byref(out)), "bg_denoiser_create")
         torch.cuda.current_stream().synchronize()   # weights / sincos may now be released or modified
-        self._handle, self._packed_sig = out, sig
+        self._handle, self._packed_sig, self._dirty = out, sig, False
 
     def _workspace(self, B, S, E, device):
         key = (B, S, E, device.index)

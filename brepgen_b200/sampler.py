@@ -40,6 +40,8 @@ class CascadeConfig:
     dense_masks: bool = False            # True: skip dedup, every slot valid (the dense-FLOP benchmark mode)
     seed: int = 0
     decode: bool = True
+    graph: str = "auto"                  # "on" | "off" | "auto": capture each DDPM loop (advance, forward, fused step) in a CUDA
+                                         # graph and replay it; auto = on for launch-bound shapes (few tokens, many steps)
 
 
 def shard_batch(global_batch: int, rank: int, world_size: int):
@@ -84,13 +86,86 @@ class Cascade:
         self.ddpm = DDPMScheduler(num_train_timesteps=1000, beta_schedule="linear", prediction_type="epsilon",
                                   beta_start=0.0001, beta_end=0.02, clip_sample=True, clip_sample_range=3)
 
+    # ------------------------------------------------------------------ one DDPM loop as a replayed CUDA graph
+    def _use_graph(self, cfg: CascadeConfig, n_steps: int, tokens: int) -> bool:
+        if cfg.graph == "on":
+            return True
+        if cfg.graph == "off":
+            return False
+        # a forward is ~105 launches from Python (~1 ms of host time); below ~100 k tokens the GPU finishes sooner than that
+        return n_steps >= 32 and tokens <= 100_000
+
+    def _loop_graph(self, cfg: CascadeConfig, timesteps, x, fwd):
+        """timesteps: 1-D int64 CPU tensor; x: (B, ...) fp32 on the device; fwd(x_in, t_dev) -> eps of a (possibly CFG-doubled)
+        batch.  The loop body of sample.py:145-153 -- [step counter / timestep advance] -> forward -> fused scheduler step
+        (CFG combine, x0, clip, posterior mean, Philox noise) -- is captured ONCE and replayed len(timesteps) times: no
+        per-step host work.  Nothing step-specific is a kernel argument: the timestep comes from a device scalar, the
+        coefficients from a device table indexed by a device counter (bg_step_advance / bg_ddpm_step_tab)."""
+        dev = self.device
+        lib = _ffi.lib()
+        T = len(timesteps)
+        B = x.shape[0]
+        xb = x.detach().float().contiguous().clone()
+        n = xb.numel()
+        coef = self.ddpm.coefficient_table(timesteps).to(dev)
+        ts = timesteps.to(device=dev, dtype=torch.int64).contiguous()
+        step = torch.full((1,), -1, dtype=torch.int32, device=dev)
+        t_cur = torch.zeros(1, dtype=torch.int64, device=dev)
+        seed, off0, stride = self.ddpm.philox_stream(n)
+        clip = float(self.ddpm.config.clip_sample_range) if self.ddpm.config.clip_sample else 0.0
+
+        def body():
+            st = _ffi.current_stream()
+            _ffi.check(lib.bg_step_advance(ts.data_ptr(), T, step.data_ptr(), t_cur.data_ptr(), st), "bg_step_advance")
+            pred = fwd(torch.cat([xb, xb], 0) if cfg.use_cf else xb, t_cur)
+            pc = pred[:B] if cfg.use_cf else pred
+            pu = pred[B:] if cfg.use_cf else None
+            _ffi.check(lib.bg_ddpm_step_tab(pc.data_ptr(), _ffi.ptr(pu), float(cfg.guidance_w), xb.data_ptr(), xb.data_ptr(),
+                                            seed, off0, stride, n, coef.data_ptr(), step.data_ptr(), clip, st),
+                       "bg_ddpm_step_tab")
+
+        # warm-up outside the capture (packs the weights, allocates the workspace), then rewind the state it touched
+        x0 = xb.clone()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        xb.copy_(x0)
+        step.fill_(-1)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            body()
+        for _ in range(T):
+            g.replay()
+        self.ddpm.advance_philox(n, T)
+        self.last_graph_steps = getattr(self, "last_graph_steps", 0) + T
+        return xb
+
     # ------------------------------------------------------------------ one denoising loop
     def _loop(self, cfg: CascadeConfig, sched, timesteps, x, fwd, label2, gen, on_step=None, noise_fn=None):
         """fwd(x_in, t_dev) -> eps for a (possibly CFG-doubled) batch; noise_fn(k, shape) -> explicit DDPM step noise"""
         B = x.shape[0]
         k = 0
-        ts_dev = timesteps.to(self.device)
         is_ddpm = isinstance(sched, DDPMScheduler)
+        if is_ddpm and noise_fn is None and gen is None and len(timesteps) > 0 and \
+                self._use_graph(cfg, len(timesteps), x[0].numel() // x.shape[-1] * B * (2 if cfg.use_cf else 1)):
+            # on_step (the late face-count increase, sample.py:140-142) changes the shape once: one graph per segment
+            lo = 0
+            ts_list = [int(t) for t in timesteps]
+            while lo < len(ts_list):
+                if on_step is not None:
+                    x = on_step(ts_list[lo], x)
+                hi = lo + 1
+                if on_step is not None:
+                    while hi < len(ts_list) and on_step(ts_list[hi], x).shape == x.shape:
+                        hi += 1
+                else:
+                    hi = len(ts_list)
+                x = self._loop_graph(cfg, timesteps[lo:hi], x, fwd)
+                lo = hi
+            return x
+        ts_dev = timesteps.to(self.device)
         for i in range(len(timesteps)):
             t = timesteps[i]
             t_dev = ts_dev[i:i + 1]
@@ -168,19 +243,17 @@ class Cascade:
         rep2 = (lambda t: torch.cat([t, t], 0)) if cfg.use_cf else (lambda t: t)
 
         # STEP 1-1 surface positions (sample.py:126-153)
-        late = {"done": cfg.use_cf}
-
         def late_increase(t, x):
-            # non-CFG runs double the face slots once the DDPM tail (t < 250) starts (sample.py:140-142)
-            if not late["done"] and (t < 0 or t <= 249):
-                late["done"] = True
+            # non-CFG runs double the face slots once the DDPM tail (t < 250) starts (sample.py:140-142).  Pure function of
+            # (t, shape): the graph path probes it to find the segment boundaries.
+            if not cfg.use_cf and x.shape[1] == S0 and (t < 0 or t <= 249):
                 return x.repeat(1, 2, 1)
             return x
 
         surfPos = noise("surfPos", (B, S0, 6))
         surfPos = self._stage(cfg, surfPos, lambda x, t: self.m["surfpos"](x, t, label2), label2, gen, True,
                               on_step=late_increase, noise_fn=nf("surfPos"), name="surfPos")
-        if not late["done"]:
+        if not cfg.use_cf and surfPos.shape[1] == S0:
             surfPos = surfPos.repeat(1, 2, 1)
 
         # STEP 1-2 duplicate faces (sample.py:159-183)

@@ -111,6 +111,22 @@ class DDPMScheduler:
             sigma = float(torch.clamp(b_prev / b_t * cur_beta, min=1e-20) ** 0.5)
         return float(b_t ** 0.5), float(a_t ** 0.5), float(c_x0), float(c_x), sigma
 
+    def coefficient_table(self, timesteps) -> torch.Tensor:
+        """[len(timesteps), 5] fp32 (CPU): step_coefficients(t) for every t of a denoising loop -- the device table that
+        bg_ddpm_step_tab indexes with its step counter when the loop is captured in a CUDA graph."""
+        rows = [self.step_coefficients(_as_int(t)) for t in timesteps]
+        return torch.tensor(rows, dtype=torch.float32).reshape(-1, 5)
+
+    def philox_stream(self, n: int):
+        """(seed, offset0, stride) of the in-kernel noise stream for a loop of steps over n elements; advances the
+        scheduler's offset past `steps` later via advance_philox."""
+        if self._philox_seed is None:
+            self._philox_seed = mix_seed(torch.initial_seed())
+        return self._philox_seed, self._philox_offset, (n + 3) // 4
+
+    def advance_philox(self, n: int, steps: int):
+        self._philox_offset += steps * ((n + 3) // 4)
+
     def step(self, model_output: torch.Tensor, timestep, sample: torch.Tensor, generator=None, return_dict: bool = True,
              noise: Optional[torch.Tensor] = None, model_output_uncond: Optional[torch.Tensor] = None,
              guidance_w: float = 0.0, out: Optional[torch.Tensor] = None):

@@ -113,6 +113,16 @@ int bg_vae_encode(BgVae* m, const float* x, int N, int hw, float* out, void* wor
 int bg_ddpm_step(const float* eps_cond, const float* eps_uncond, float cfg_w, const float* x, float* out,
                  const float* noise, uint64_t seed, uint64_t offset, int64_t n, float sqrt_one_minus_abar,
                  float sqrt_abar, float clip, float c_x0, float c_x, float sigma, void* stream);
+/* The same update in table-driven form for CUDA-graph capture of a whole denoising loop: no
+ * step-specific value is a kernel argument.  coef_table[k][5] = (sqrt(1-abar_t), sqrt(abar_t), c_x0, c_x, sigma) of step k
+ * (device, built once per loop from the scheduler's host tables); *step (device int32) = the current step index;
+ * in-kernel Philox noise with counter offset0 + k * offset_stride.  Replaces the loop body sample.py:145-153. */
+int bg_ddpm_step_tab(const float* eps_cond, const float* eps_uncond, float cfg_w, const float* x, float* out, uint64_t seed,
+                     uint64_t offset0, uint64_t offset_stride, int64_t n, const float* coef_table, const int32_t* step,
+                     float clip, void* stream);
+/* k = ++(*step) (clamped to n_steps - 1);  *t_cur = timesteps[k].  One tiny kernel at the top of every captured step: the
+ * denoiser forward reads its timestep from t_cur (device int64), bg_ddpm_step_tab reads k. */
+int bg_step_advance(const int64_t* timesteps, int n_steps, int32_t* step, int64_t* t_cur, void* stream);
 /* out = c_sample*x - c_eps*(w0*e0 + w1*e1 + w2*e2 + w3*e3)    (PNDM transfer + Adams-Bashforth / RK combination;
  * unused e_i may be NULL with w_i = 0) */
 int bg_pndm_step(const float* x, float* out, int64_t n, float c_sample, float c_eps, const float* e0, float w0,
@@ -144,6 +154,35 @@ int bg_op_attention(const void* qkv, void* out, int B, int L, const uint8_t* key
 int bg_op_layernorm_f16(const float* x, int ldx, const float* gamma, const float* beta, void* y, int ldy, int rows,
                         int act, void* stream);
 int bg_op_cast_f16(const float* x, void* y, int64_t n, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Post-decode geometry glue: the numeric cores of the per-CAD post-processing between the VAE
+ * decoders and OpenCASCADE.  The list / set bookkeeping around them stays on the host (brepgen_b200/postprocess.py, same
+ * function names and return values as utils.py); construct_brep (utils.py:819) is out of scope.  All pointers are device
+ * pointers; fp32 / int32.
+ * ------------------------------------------------------------------------------------------------------------- */
+/* sample.py:316-329 (+ utils.py:48-59): out[e][0|1][3] = edge_ncs[e][0|31] * (bsize / 2) + bcenter of the edge box
+ * edge_pos[e][6] * pos_scale (bsize = largest extent) */
+int bg_edge_endpoints(const float* edge_ncs, const float* edge_pos, float pos_scale, int64_t n_edges, float* out, void* stream);
+/* nn[i] = index of the nearest point of ANOTHER group inside the same segment [seg_off[s], seg_off[s+1]) (lowest index on
+ * ties, -1 if none): utils.py:403-421 (edge2loop: group = edge, segment = face) and :505-524 (group = face, segment = CAD) */
+int bg_nn_exclude(const float* pts, const int32_t* group, const int32_t* seg_off, int n_seg, int32_t* nn, void* stream);
+/* out[i][j] = |pts_i - pts_j| < threshold (n x n): utils.py:556-561 */
+int bg_pairs_within(const float* pts, int n, float threshold, uint8_t* out, void* stream);
+/* out[i][j] = i != j && set(adj_i) == set(adj_j) && mean|z_i - z_j| < threshold (n x n): utils.py:607-619 */
+int bg_edge_pair_match(const int32_t* edge_vertex_adj, const float* z, int z_dim, int n, float threshold, uint8_t* out,
+                       void* stream);
+/* utils.py:692-728: fit every decoded edge curve edge_ncs[e][32][3] to its two vertices vertex_se[e][2][3] */
+int bg_edge_fit(const float* edge_ncs, const float* vertex_se, int n_edges, float* edge_wcs, void* stream);
+/* utils.py:732-752: initial surface grids surf_wcs[f][32*32][3]; face f owns the edges adj[adj_off[f] .. adj_off[f+1]) */
+int bg_surf_init(const float* surf_ncs, const float* surf_pos, const float* edge_wcs, const int32_t* adj_off, const int32_t* adj,
+                 int n_faces, float* surf_wcs, void* stream);
+/* utils.py:756-770: `iters` AdamW steps on one translation per face minimising the wire -> surface Chamfer distance, all
+ * faces and all iterations in ONE launch; inv_nface[f] = 1 / (number of faces of f's CAD) (the loss is a mean over the CAD's
+ * faces).  surf_out = surf_init + the offset before the last step (what the reference returns); offset_out may be NULL. */
+int bg_surf_offset_opt(const float* surf_init, const float* edge_wcs, const int32_t* adj_off, const int32_t* adj,
+                       const float* inv_nface, int n_faces, int max_edges_per_face, int iters, float lr, float beta1, float beta2,
+                       float eps, float weight_decay, float* surf_out, float* offset_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -150,9 +150,16 @@ def test_hybrid_schedule_runs_and_counts_steps():
             counts[_k] = counts.get(_k, 0) + 1
             return _o(*a, **kw)
         m.forward = wrapped
-    cfg = CascadeConfig(batch_size=1, num_surfaces=3, num_edges=2, schedule="reference", decode=False)
+    cfg = CascadeConfig(batch_size=1, num_surfaces=3, num_edges=2, schedule="reference", decode=False, graph="off")
     out = Cascade(ms).run(cfg)
     assert counts == {"surfpos": 408, "surfz": 209, "edgepos": 408, "edgez": 209}
+    # with CUDA graphs the two 250-step DDPM tails are captured once (warm-up + capture = 2 python-level forwards each) and
+    # replayed; the PNDM parts stay eager
+    counts.clear()
+    casc = Cascade(ms)
+    out_g = casc.run(CascadeConfig(batch_size=1, num_surfaces=3, num_edges=2, schedule="reference", decode=False, graph="on"))
+    assert counts == {"surfpos": 160, "surfz": 209, "edgepos": 160, "edgez": 209} and casc.last_graph_steps == 500
+    assert out_g["surfPos"].shape == out["surfPos"].shape
     assert out["surfPos"].shape == (1, 6, 6) and out["edgeV"].shape == (1, 6, 2, 6)
     assert all(torch.isfinite(v.float()).all() for v in out.values())
 
