@@ -47,9 +47,12 @@ def parse():
     ap.add_argument("--cf", action="store_true", help="classifier-free guidance (furniture config: 2x forward batch, no late increase)")
     ap.add_argument("--schedule", default="ddpm", choices=["ddpm", "reference"],
                     help="ddpm = N DDPM steps per stage (the metric's definition); reference = the shipped PNDM/DDPM hybrid")
-    ap.add_argument("--masks", default="dense", choices=["dense", "flow"],
+    ap.add_argument("--masks", default="dense", choices=["dense", "flow", "ragged"],
                     help="dense = every slot valid, the metric's dense-FLOP mode; flow = run both dedups (sample.py:159-183,242-261) "
-                         "and mask what they remove (fully padded key blocks are then skipped)")
+                         "and mask what they remove; ragged = synthetic masks shaped like a trained model's output (1/8..1/2 of "
+                         "the faces, 3..E/3 edges per face valid; random-init weights never produce duplicates for flow to remove)")
+    ap.add_argument("--compact", type=int, default=1, choices=[0, 1],
+                    help="mask-aware token compaction in the denoisers (1, default) or the dense layout with masking only (0)")
     ap.add_argument("--workload", default="cascade", choices=["cascade", "surfpos"],
                     help="cascade = the metric's workload (BASELINE configs[2]); surfpos = BASELINE configs[1]: SurfPosNet, "
                          "1000-step DDPM, 30 face tokens, batch 64 (first stage only), eager loop vs CUDA-graph replay")
@@ -73,6 +76,19 @@ def encoder_flops(L):   # per sample, per forward, dense, mul-ad
 
 def mlp_flops(d_in, d_out):
     return 2 * d_in * 768 + 2 * 768 * d_out
+
+
+def cascade_flops_valid_tokens(S0, S, E, surf_mask, edge_mask, steps=1000):
+    """the same formulas with L -> L_valid per sample (mean over the batch).  SurfPos has no mask; SurfZ attends
+    over the valid faces; EdgePos over (valid faces) x E (face mask repeated, network.py:1268); EdgeZ over the valid edges."""
+    sv = (~surf_mask).sum(1).double()
+    ev = (~edge_mask).sum((1, 2)).double()
+    enc = lambda L: 12 * (L * 7_864_320 + 3072 * L * L)
+    sp = lambda s: encoder_flops(s) + s * (mlp_flops(6, 768) + mlp_flops(768, 6))
+    sz = enc(sv) + sv * (mlp_flops(48, 768) + mlp_flops(6, 768) + mlp_flops(768, 48))
+    ep = enc(sv * E) + sv * (mlp_flops(6, 768) + mlp_flops(48, 768)) + sv * E * (mlp_flops(6, 768) + mlp_flops(768, 6))
+    ez = enc(ev) + sv * (mlp_flops(6, 768) + mlp_flops(48, 768)) + ev * (2 * mlp_flops(6, 768) + mlp_flops(12, 768) + mlp_flops(768, 18))
+    return float(steps * (0.75 * sp(S0) + 0.25 * sp(S) + (sz + ep + ez).mean()))
 
 
 def cascade_flops_per_brep(S0, S, E, steps=1000):
@@ -311,9 +327,12 @@ def main():
         surf_vae, edge_vae = build_synthetic_decoders(dev)
     except ImportError:
         pass
+    for m in models.values():
+        m.compact = args.compact
     casc = Cascade(models, surf_vae, edge_vae, device=dev)
     cfg = CascadeConfig(batch_size=B, num_surfaces=S0, num_edges=E, use_cf=args.cf, class_label=6, schedule=args.schedule,
-                        ddpm_steps=T, dense_masks=args.masks == "dense", seed=1000 + rank, decode=surf_vae is not None)
+                        ddpm_steps=T, dense_masks=args.masks == "dense", ragged_masks=args.masks == "ragged", seed=1000 + rank,
+                        decode=surf_vae is not None)
     g = torch.Generator().manual_seed(1000 + rank)
     shapes = {"surfPos": (B, S0, 6), "surfZ": (B, S, 48), "edgePos": (B, S, E, 6), "edgeZV": (B, S, E, 18)}
     host_in = {k: torch.randn(s, generator=g).pin_memory() for k, s in shapes.items()}
@@ -340,7 +359,10 @@ def main():
         barrier()
         return ms
 
-    step_resident = lambda: casc.run(cfg, init_noise=dev_in)
+    last = {}
+
+    def step_resident():
+        last["out"] = casc.run(cfg, init_noise=dev_in)
     for _ in range(args.warmup):
         step_resident()
     clocks = Clocks(local)
@@ -366,21 +388,38 @@ def main():
     e2e = None
     if not args.no_e2e:
         host_out = {}
+        gather_ms = []
+        from brepgen_b200.sampler import gather_outputs
 
         def step_e2e():
             din = {k: v.to(dev, non_blocking=True) for k, v in host_in.items()}
             out = casc.run(cfg, init_noise=din)
+            if dist is not None:
+                # BASELINE configs[3]: the final all_gather of every output over NCCL (NVLink / NVSwitch), inside the timed
+                # region; its own duration is recorded with CUDA events on the same stream
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record()
+                gathered = gather_outputs(out)
+                g1.record()
+                gather_ms.append((g0, g1))
+                del gathered
             for k, v in out.items():
                 if k not in host_out:
                     host_out[k] = torch.empty(v.shape, dtype=v.dtype).pin_memory()
                 host_out[k].copy_(v, non_blocking=True)
             torch.cuda.current_stream().synchronize()
         step_e2e()
+        gather_ms.clear()
         ms_e = timed(step_e2e, args.steps)
+        ms_g = sum(a.elapsed_time(b) for a, b in gather_ms) / max(len(gather_ms), 1) if gather_ms else 0.0
         h2d = sum(v.numel() * v.element_size() for v in host_in.values())
         d2h = sum(v.numel() * v.element_size() for v in host_out.values())
-        e2e = {"value": world * B / (norm_ms(ms_e) / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "ms_per_step": ms_e}
+        # the gather, like the decodes, happens once per cascade whatever T is: kept out of the 1000 / T scaling
+        norm_e = (ms_e - ms_dec - ms_g) * scale + ms_dec + ms_g
+        e2e = {"value": world * B / (norm_e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": ms_e,
+               "final_all_gather_ms": ms_g if dist is not None else None,
+               "all_gather_bytes_per_rank": d2h * world if dist is not None else 0}
 
     # roofline of the dominant kernel (edge-stage flash attention, L = S*E), timed alone with CUDA events
     burst, sustained, src = peaks()
@@ -410,7 +449,16 @@ def main():
     # CFG doubles every forward; the shipped hybrid runs 158 PNDM + 250 DDPM forwards per stage (sample.py:128-155)
     flops_brep = cascade_flops_per_brep(S0, S, E, steps=1000 if args.schedule == "ddpm" else 408) * (2 if args.cf else 1)
     whole = {"algorithmic_tflop_per_brep": flops_brep / 1e12, "achieved_tflops_per_gpu": value / world * flops_brep / 1e12,
-             "frac_of_sustained_peak": value / world * flops_brep / 1e12 / sustained}
+             "frac_of_sustained_peak": value / world * flops_brep / 1e12 / sustained,
+             "flops": "dense-algorithmic (SURVEY.md 8d): every face / edge slot counted, masks or not"}
+    if args.masks != "dense" and "out" in last:
+        o = last["out"]
+        fv = cascade_flops_valid_tokens(S0, S, E, o["surfMask"].cpu(), o["edgeM"].cpu(),
+                                        steps=1000 if args.schedule == "ddpm" else 408) * (2 if args.cf else 1)
+        whole["valid_token_tflop_per_brep"] = fv / 1e12
+        whole["valid_token_achieved_tflops_per_gpu"] = value / world * fv / 1e12
+        whole["valid_token_frac_of_sustained_peak"] = value / world * fv / 1e12 / sustained
+        whole["valid_fraction_of_edge_tokens"] = float((~o["edgeM"]).float().mean())
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -427,7 +475,7 @@ def main():
                            "ddpm_steps_per_stage_timed": T, "value_normalised_to_steps_per_stage": 1000,
                            "vae_decode_in_step": surf_vae is not None, "vae_decode_ms_per_step": ms_dec,
                            "l2": "activations of one step (GBs) exceed the 126 MB L2; no explicit flush",
-                           "precision": models["surfpos"].precision, "parallelism": f"batch-sharded x{world}, no collective"},
+                           "precision": models["surfpos"].precision, "token_compaction": bool(args.compact), "parallelism": f"batch-sharded x{world}, no collective"},
                 "roofline": roofline, "whole_cascade": whole, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clk}
         print(json.dumps(line))

@@ -20,7 +20,7 @@ class BgNamedTensor(C.Structure):
 
 class BgDenoiserArgs(C.Structure):
     _fields_ = [("B", i32), ("S", i32), ("E", i32), ("x", vp), ("timesteps", vp), ("n_timesteps", i32),
-                ("surfPos", vp), ("surfZ", vp), ("edgePos", vp), ("mask", vp), ("class_label", vp), ("out", vp)]
+                ("surfPos", vp), ("surfZ", vp), ("edgePos", vp), ("mask", vp), ("class_label", vp), ("out", vp), ("compact", i32)]
 
 
 # name -> (restype, argtypes); every symbol include/brepgen_b200.h declares (tests check the export list against this)

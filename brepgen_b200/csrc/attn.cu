@@ -68,6 +68,8 @@ struct AttnParams {
   const int* blk_list;
   const int* blk_count;
   const uint32_t* blk_words;   // [B][nkb][4] invalid-key bit words of the listed blocks, list order (per forward), or null
+  const int* seq_row0;         // variable-length mode: first row / number of rows of every sample, or null (dense)
+  const int* seq_len;
   float scale_log2;   // log2(e) / sqrt(64)
   int pingpong;       // XU token between the two softmax warpgroups (named barriers)
   int probe;          // early non-blocking mbarrier probes
@@ -102,7 +104,14 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int qgrp = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int nblk = p.blk_count ? p.blk_count[b] : p.nkb;
+  // QKV / out are addressed as ONE [rows][cols] matrix; sample b owns rows [row0, row0 + len).  Dense: row0 = b * L, len = L.
+  // Variable-length mode (mask-aware token compaction): rows of the valid tokens only, packed back to back.  A tile may then
+  // run into the next sample's rows (or past the end: TMA zero-fills): those keys are masked (key >= len), those query rows
+  // are never written.
+  const int row0 = p.seq_row0 ? p.seq_row0[b] : b * p.L;
+  const int len = p.seq_len ? p.seq_len[b] : p.L;
+  if (qgrp * NT * 128 >= len) return;     // variable-length mode: the grid is sized for the longest sample
+  const int nblk = p.blk_count ? p.blk_count[b] : (len + 127) / 128;
   const int* blist = p.blk_list ? p.blk_list + (size_t)b * p.nkb : nullptr;
 
   constexpr int PRODUCER_WARP = NT * 4;
@@ -128,13 +137,13 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
     // allocation, the mask-word construction and the CTA-wide synchronisation below
     mbar_arrive_expect_tx(q_full, NT * TILE_BYTES);
     for (int t = 0; t < NT; ++t)
-      tma_load_3d(smem + C::OFF_Q + t * TILE_BYTES, &tmQKV, q_full, h * DH, (qgrp * NT + t) * 128, b);
+      tma_load_2d(smem + C::OFF_Q + t * TILE_BYTES, &tmQKV, q_full, h * DH, row0 + (qgrp * NT + t) * 128);
     for (int it = 0; it < nblk && it < C::ST; ++it) {
       const int kb = blist ? blist[it] : it;
       mbar_arrive_expect_tx(&k_full[it], TILE_BYTES);
-      tma_load_3d(smem + C::OFF_K + it * TILE_BYTES, &tmQKV, &k_full[it], DMODEL + h * DH, kb * 128, b);
+      tma_load_2d(smem + C::OFF_K + it * TILE_BYTES, &tmQKV, &k_full[it], DMODEL + h * DH, row0 + kb * 128);
       mbar_arrive_expect_tx(&v_full[it], TILE_BYTES);
-      tma_load_3d(smem + C::OFF_V + it * TILE_BYTES, &tmQKV, &v_full[it], 2 * DMODEL + h * DH, kb * 128, b);
+      tma_load_2d(smem + C::OFF_V + it * TILE_BYTES, &tmQKV, &v_full[it], 2 * DMODEL + h * DH, row0 + kb * 128);
     }
   }
   if (warp == MMA_WARP) tmem_alloc<C::TMEM_COLS>(tmem_slot);
@@ -151,7 +160,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
           w = p.blk_words[((size_t)b * p.nkb + (wi >> 2)) * 4 + (wi & 3)];
         } else {
           const int base = (wi >> 2) * 128 + (wi & 3) * 32;
-          w = base + 32 <= p.L ? 0u : (base >= p.L ? 0xffffffffu : (0xffffffffu << (p.L - base)));
+          w = base + 32 <= len ? 0u : (base >= len ? 0xffffffffu : (0xffffffffu << (len - base)));
         }
         maskw[wi] = w;
       }
@@ -159,7 +168,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
       for (int wi = warp; wi < nblk * 4; wi += PRODUCER_WARP) {
         const int kb = blist ? blist[wi >> 2] : (wi >> 2);
         const int key = kb * 128 + (wi & 3) * 32 + lane;
-        bool bad = key >= p.L;
+        bool bad = key >= len;
         if (!bad && p.key_mask) bad = p.key_mask[(size_t)b * p.L + key] != 0;
         const uint32_t w = __ballot_sync(0xffffffffu, bad);
         if (lane == 0) maskw[wi] = w;
@@ -200,10 +209,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
         const uint32_t par = ((it / C::ST) & 1) ^ 1;
         mbar_wait(&k_empty[s], par);
         mbar_arrive_expect_tx(&k_full[s], TILE_BYTES);
-        tma_load_3d(smem + C::OFF_K + s * TILE_BYTES, &tmQKV, &k_full[s], DMODEL + h * DH, kb * 128, b);
+        tma_load_2d(smem + C::OFF_K + s * TILE_BYTES, &tmQKV, &k_full[s], DMODEL + h * DH, row0 + kb * 128);
         mbar_wait(&v_empty[s], par);
         mbar_arrive_expect_tx(&v_full[s], TILE_BYTES);
-        tma_load_3d(smem + C::OFF_V + s * TILE_BYTES, &tmQKV, &v_full[s], 2 * DMODEL + h * DH, kb * 128, b);
+        tma_load_2d(smem + C::OFF_V + s * TILE_BYTES, &tmQKV, &v_full[s], 2 * DMODEL + h * DH, row0 + kb * 128);
       }
     }
    } else if (warp < MMA_WARP + NT) {
@@ -411,9 +420,9 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
       for (int i = 0; i < DH; ++i) o[i] = 0.f;
     }
     const int row = (qgrp * NT + t) * 128 + r;
-    if (row < p.L) {
+    if (row < len) {
       const float inv = l > 0.f ? 1.f / l : 0.f;
-      uint4* dst = reinterpret_cast<uint4*>(p.out + ((size_t)b * p.L + row) * p.ldo + h * DH);
+      uint4* dst = reinterpret_cast<uint4*>(p.out + ((size_t)row0 + row) * p.ldo + h * DH);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         __half2 h0 = __floats2half2_rn(o[8 * q] * inv, o[8 * q + 1] * inv);
@@ -491,10 +500,13 @@ int launch_attention(cudaStream_t st, const AttnArgs& a) {
   BG_REQUIRE(a.L <= 128 * ACfg<2>::MAX_KB, "attention: sequence longer than 8192 tokens is not supported");
   BG_REQUIRE((a.blk_list == nullptr) == (a.blk_count == nullptr), "attention: blk_list and blk_count go together");
   CUtensorMap tm;
-  BG_TRY(make_tmap_3d_f16(&tm, a.qkv, (uint64_t)a.B, (uint64_t)a.L, 3 * DMODEL, 3 * DMODEL, 128));
+  BG_REQUIRE((a.seq_row0 == nullptr) == (a.seq_len == nullptr), "attention: seq_row0 and seq_len go together");
+  BG_REQUIRE(a.seq_len == nullptr || (a.key_mask == nullptr && a.blk_list == nullptr), "attention: variable-length mode takes no mask");
+  BG_TRY(make_tmap_2d_f16(&tm, a.qkv, (uint64_t)a.B * (uint64_t)a.L, 3 * DMODEL, 3 * DMODEL, 128));
   AttnParams p;
   p.out = a.out; p.ldo = a.ldo; p.B = a.B; p.L = a.L; p.nkb = (a.L + 127) / 128;
   p.key_mask = a.key_mask; p.blk_list = a.blk_list; p.blk_count = a.blk_count; p.blk_words = a.blk_words;
+  p.seq_row0 = a.seq_row0; p.seq_len = a.seq_len;
   p.scale_log2 = 1.4426950408889634f / 8.0f;
   static int poly = -1, ptmem = 1, pingpong = 1;   // environment knobs, read once per process
   if (poly < 0) {

@@ -66,6 +66,8 @@ struct GemmEpilogue {
   int rows_per_vec = 1;
   int ldv = 0;
   int a_kwrap = 0;               // >0: A has a_kwrap columns and is reused cyclically along K (split-weight GEMM)
+  const int* m_dev = nullptr;    // optional device int: only min(M, *m_dev) rows are computed (token compaction)
+  const int* row_map = nullptr;  // optional: rowvec is indexed with row_map[row] / rows_per_vec instead of row / rows_per_vec
 };
 int launch_gemm_f16(cudaStream_t st, const __half* A, int lda, const __half* W, int ldw, int M, int N, int K,
                     const GemmEpilogue& ep);
@@ -80,6 +82,10 @@ struct AttnArgs {
   const int* blk_list = nullptr;       // [B, nkb] key blocks (of 128) with >=1 valid key, or null = all
   const int* blk_count = nullptr;      // [B]
   const uint32_t* blk_words = nullptr; // [B, nkb, 4] invalid-key bit words in LIST order (launch_build_block_list), or null
+  // variable-length mode (token compaction): sample b owns rows [seq_row0[b], seq_row0[b] + seq_len[b]) of qkv / out, all of
+  // them valid; L = the maximum length (grid size); key_mask / blk_* must be null
+  const int* seq_row0 = nullptr;
+  const int* seq_len = nullptr;
 };
 int launch_attention(cudaStream_t st, const AttnArgs& a);
 int launch_attention_rowsplit(cudaStream_t st, const AttnArgs& a, int poly);   // attn_rs.cu, L > 128 only
@@ -92,14 +98,22 @@ int launch_build_block_list(cudaStream_t st, const uint8_t* key_mask, int B, int
 // ---- CUDA-core kernels (HBM-bound glue) ----
 // y[row, 0:768] (fp16, pitch ldy) = act(LayerNorm(x[row, 0:768]) * g + b); act: 0 none, 1 SiLU.   eps = 1e-5
 // lo_offset > 0: additionally writes the fp16 rounding residual (value - fp16(value)) at y[row, lo_offset + c]
+// rows_dev (optional): device int, the kernel processes min(rows, *rows_dev) rows (token compaction)
 int launch_layernorm_f16(cudaStream_t st, const float* x, int ldx, const float* g, const float* b, __half* y, int ldy,
-                         int rows, int act, int lo_offset = 0);
+                         int rows, int act, int lo_offset = 0, const int* rows_dev = nullptr);
 // y (fp16, pitch ldy) = SiLU(LayerNorm(x[row,0:d_in] * W0^T + b0)); W0t is [d_in][768] fp32 (transposed Linear weight)
+// row_map (optional): output row r reads input row row_map[r] (gather of the valid tokens)
 int launch_embed_in(cudaStream_t st, const float* x, int ldx, int d_in, const float* W0t, const float* b0, const float* g,
-                    const float* b, __half* y, int ldy, int rows);
+                    const float* b, __half* y, int ldy, int rows, const int* rows_dev = nullptr, const int* row_map = nullptr);
 // out[row, 0:d_out] (fp32) = SiLU(LayerNorm(x[row, 0:768])) * W^T + bias, all fp32;  W [d_out][768], d_out <= 64
+// row_map (optional): input row r is written to output row row_map[r] (scatter back to the padded layout)
 int launch_ln_silu_head(cudaStream_t st, const float* x, int ldx, const float* g, const float* b, const float* W,
-                        const float* bias, float* out, int d_out, int rows);
+                        const float* bias, float* out, int d_out, int rows, const int* rows_dev = nullptr,
+                        const int* row_map = nullptr);
+// valid-token compaction of a [B, L] key-padding mask: seq_len[b], seq_row0[b] (exclusive prefix), *m_valid (total) and
+// row_map[compact row] = b * L + token
+int launch_zero_rows_f16(cudaStream_t st, __half* y, int ld, int cols, const int* row0_dev, int nrows, int max_rows);
+int launch_compact(cudaStream_t st, const uint8_t* mask, int B, int L, int* seq_len, int* seq_row0, int* m_valid, int* row_map);
 // cond[b, :] = time_table[t_b, :] + (class_table ? class_table[label_b, :] : 0);  t: int64 [n_t] (n_t = 1 or B)
 int launch_cond(cudaStream_t st, const float* time_table, const int64_t* t, int n_t, const float* class_table,
                 const int64_t* label, float* cond, int B);

@@ -324,6 +324,7 @@ struct Workspace {
   uint8_t* mask;
   int *blk_list, *blk_count;
   uint32_t* blk_words;
+  int *row_map, *seq_len, *seq_row0, *m_valid;   // token compaction
   size_t bytes;
 };
 
@@ -350,6 +351,10 @@ Workspace carve(char* base, int kind, int B, int S, int E) {
   w.blk_list = reinterpret_cast<int*>(take((size_t)B * nkb * 4));
   w.blk_count = reinterpret_cast<int*>(take((size_t)B * 4));
   w.blk_words = reinterpret_cast<uint32_t*>(take((size_t)B * nkb * 16));
+  w.row_map = reinterpret_cast<int*>(take(M * 4));
+  w.seq_len = reinterpret_cast<int*>(take((size_t)B * 4));
+  w.seq_row0 = reinterpret_cast<int*>(take((size_t)B * 4));
+  w.m_valid = reinterpret_cast<int*>(take(4));
   w.bytes = off;
   return w;
 }
@@ -425,6 +430,26 @@ int bg_denoiser_forward(BgDenoiser* m, const BgDenoiserArgs* a, void* workspace,
   BG_TRY(launch_cond(st, m->time_table, a->timesteps, a->n_timesteps, m->use_cf ? m->class_table : nullptr,
                      a->class_label, w.cond, B));
 
+  // key-padding mask (face mask repeated over edges for EdgePosNet, network.py:1268); with compaction the valid tokens are
+  // gathered: everything below runs on *m_valid rows (device-side count, no host synchronisation)
+  const uint8_t* kmask = nullptr;
+  if (kind >= 1 && a->mask) {
+    if (kind == 2) {
+      BG_TRY(launch_mask_expand(st, a->mask, w.mask, BS, E));
+      kmask = w.mask;
+    } else {
+      kmask = a->mask;
+    }
+  }
+  const bool compact = a->compact != 0 && kmask != nullptr;
+  const int* m_dev = nullptr;
+  const int* row_map = nullptr;
+  if (compact) {
+    BG_TRY(launch_compact(st, kmask, B, L, w.seq_len, w.seq_row0, w.m_valid, w.row_map));
+    m_dev = w.m_valid;
+    row_map = w.row_map;
+  }
+
   // 2. embeddings -> X
   const float* srcs[6] = {a->x, a->surfPos, a->surfZ, a->edgePos, a->x, a->x ? a->x + 12 : nullptr};
   const int src_ld[6] = {kd.x_width, 6, 48, 6, 18, 18};
@@ -439,7 +464,7 @@ int bg_denoiser_forward(BgDenoiser* m, const BgDenoiserArgs* a, void* workspace,
       ++i_face;
     } else {
       BG_TRY(launch_embed_in(st, srcs[e.src], src_ld[e.src], e.d_in, W.w0t, W.b0, W.lng, W.lnb, Htok + i_tok * D,
-                             m->n_tok * D, M));
+                             m->n_tok * D, M, m_dev, row_map));
       ++i_tok;
     }
   }
@@ -457,27 +482,23 @@ int bg_denoiser_forward(BgDenoiser* m, const BgDenoiserArgs* a, void* workspace,
     GemmEpilogue ep;
     ep.out = w.X; ep.ldo = D; ep.out_f16 = 0; ep.bias = m->bcat_tok;
     ep.rowvec = tokvec; ep.rows_per_vec = tok_rpv; ep.ldv = D;
+    ep.m_dev = m_dev; ep.row_map = row_map;       // compaction: row r carries source token row_map[r]
     BG_TRY(launch_gemm_f16(st, Htok, m->n_tok * D, m->wcat_tok, m->n_tok * D, M, D, m->n_tok * D, ep));
   }
 
-  // 3. key-padding mask (face mask repeated over edges for EdgePosNet, network.py:1268) and valid key-block list
-  const uint8_t* kmask = nullptr;
-  if (kind >= 1 && a->mask) {
-    if (kind == 2) {
-      BG_TRY(launch_mask_expand(st, a->mask, w.mask, BS, E));
-      kmask = w.mask;
-    } else {
-      kmask = a->mask;
-    }
-    BG_TRY(launch_build_block_list(st, kmask, B, L, w.blk_list, w.blk_count, w.blk_words));
-  }
+  // 3. valid key-block list (dense layout only: after compaction every key of a sample's rows is valid)
+  if (kmask && !compact) BG_TRY(launch_build_block_list(st, kmask, B, L, w.blk_list, w.blk_count, w.blk_words));
+  // compaction: the last sample's final key tile reads up to 127 rows past the last valid token; the QKV GEMMs never write
+  // them, so clear them once (the embed stage above used this buffer as scratch)
+  if (compact) BG_TRY(launch_zero_rows_f16(st, w.QKV, 3 * D, 3 * D, w.m_valid, 128, M));
 
   // 4. encoder
   for (int i = 0; i < NLAYER; ++i) {
     const LayerW& Lw = m->layer[i];
-    BG_TRY(launch_layernorm_f16(st, w.X, D, Lw.ln1g, Lw.ln1b, w.Xn, D, M, 0));
+    BG_TRY(launch_layernorm_f16(st, w.X, D, Lw.ln1g, Lw.ln1b, w.Xn, D, M, 0, 0, m_dev));
     {
       GemmEpilogue ep;
+      ep.m_dev = m_dev;
       ep.out = w.QKV; ep.ldo = 3 * D; ep.out_f16 = 1; ep.bias = Lw.bqkv;
       ep.a_kwrap = Lw.kqk > D ? D : 0;
       BG_TRY(launch_gemm_f16(st, w.Xn, D, Lw.wqk, Lw.kqk, M, 2 * D, Lw.kqk, ep));     // q | k
@@ -487,27 +508,35 @@ int bg_denoiser_forward(BgDenoiser* m, const BgDenoiserArgs* a, void* workspace,
     }
     {
       AttnArgs at;
-      at.qkv = w.QKV; at.out = w.AO; at.ldo = D; at.B = B; at.L = L; at.key_mask = kmask;
-      at.blk_list = kmask ? w.blk_list : nullptr;
-      at.blk_count = kmask ? w.blk_count : nullptr;
-      at.blk_words = kmask ? w.blk_words : nullptr;
+      at.qkv = w.QKV; at.out = w.AO; at.ldo = D; at.B = B; at.L = L;
+      if (compact) {
+        at.seq_row0 = w.seq_row0; at.seq_len = w.seq_len;
+      } else {
+        at.key_mask = kmask;
+        at.blk_list = kmask ? w.blk_list : nullptr;
+        at.blk_count = kmask ? w.blk_count : nullptr;
+        at.blk_words = kmask ? w.blk_words : nullptr;
+      }
       BG_TRY(launch_attention(st, at));
     }
     {
       GemmEpilogue ep;
+      ep.m_dev = m_dev;
       ep.out = w.X; ep.ldo = D; ep.out_f16 = 0; ep.bias = Lw.bo; ep.resid = w.X; ep.ldr = D;
       ep.a_kwrap = Lw.ko > D ? D : 0;
       BG_TRY(launch_gemm_f16(st, w.AO, D, Lw.wo, Lw.ko, M, D, Lw.ko, ep));
     }
-    BG_TRY(launch_layernorm_f16(st, w.X, D, Lw.ln2g, Lw.ln2b, w.Xn, D, M, 0));
+    BG_TRY(launch_layernorm_f16(st, w.X, D, Lw.ln2g, Lw.ln2b, w.Xn, D, M, 0, 0, m_dev));
     {
       GemmEpilogue ep;
+      ep.m_dev = m_dev;
       ep.out = w.Hff; ep.ldo = FF; ep.out_f16 = 1; ep.relu = 1; ep.bias = Lw.b1;
       ep.a_kwrap = Lw.k1 > D ? D : 0;
       BG_TRY(launch_gemm_f16(st, w.Xn, D, Lw.w1, Lw.k1, M, FF, Lw.k1, ep));
     }
     {
       GemmEpilogue ep;
+      ep.m_dev = m_dev;
       ep.out = w.X; ep.ldo = D; ep.out_f16 = 0; ep.bias = Lw.b2; ep.resid = w.X; ep.ldr = D;
       ep.a_kwrap = Lw.k2 > FF ? FF : 0;
       BG_TRY(launch_gemm_f16(st, w.Hff, FF, Lw.w2, Lw.k2, M, D, Lw.k2, ep));
@@ -518,18 +547,20 @@ int bg_denoiser_forward(BgDenoiser* m, const BgDenoiserArgs* a, void* workspace,
   //    precision >= 1 it runs as a compensated fp16 product (hi/lo activations x hi/lo weights) and an fp32 head.
   {
     GemmEpilogue ep;
+    ep.m_dev = m_dev;
     ep.out = w.X; ep.ldo = D; ep.out_f16 = 0; ep.bias = m->fc0b;
     if (m->precision >= 1) {
       __half* A3 = w.QKV;   // [M][2304] scratch: cols 0..767 hi, 768..1535 lo (the third K block wraps back to hi)
-      BG_TRY(launch_layernorm_f16(st, w.X, D, m->normg, m->normb, A3, 3 * D, M, 0, D));
+      BG_TRY(launch_layernorm_f16(st, w.X, D, m->normg, m->normb, A3, 3 * D, M, 0, D, m_dev));
       ep.a_kwrap = 2 * D;
       BG_TRY(launch_gemm_f16(st, A3, 3 * D, m->fc0w, 3 * D, M, D, 3 * D, ep));
     } else {
-      BG_TRY(launch_layernorm_f16(st, w.X, D, m->normg, m->normb, w.Xn, D, M, 0));
+      BG_TRY(launch_layernorm_f16(st, w.X, D, m->normg, m->normb, w.Xn, D, M, 0, 0, m_dev));
       BG_TRY(launch_gemm_f16(st, w.Xn, D, m->fc0w, D, M, D, D, ep));
     }
   }
-  BG_TRY(launch_ln_silu_head(st, w.X, D, m->fclng, m->fclnb, m->fc3w, m->fc3b, a->out, kd.d_out, M));
+  if (compact) BG_CUDA(cudaMemsetAsync(a->out, 0, (size_t)M * kd.d_out * sizeof(float), st));   // padded tokens: 0
+  BG_TRY(launch_ln_silu_head(st, w.X, D, m->fclng, m->fclnb, m->fc3w, m->fc3b, a->out, kd.d_out, M, m_dev, row_map));
   return BG_OK;
 }
 

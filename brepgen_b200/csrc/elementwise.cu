@@ -70,9 +70,11 @@ __device__ __forceinline__ void store_row_f16(const float (&v)[24], __half* y, i
 
 __global__ void __launch_bounds__(256) layernorm_f16_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ g,
                                                             const float* __restrict__ b, __half* __restrict__ y, int ldy,
-                                                            int rows, int act, int lo_offset) {
+                                                            int rows, int act, int lo_offset,
+                                                            const int* __restrict__ rows_dev) {
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
+  if (rows_dev) rows = min(rows, *rows_dev);      // token compaction: the number of valid rows lives on the device
   for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
     const float* xr = x + (size_t)row * ldx;
     float v[24];
@@ -90,11 +92,13 @@ __global__ void __launch_bounds__(256) layernorm_f16_kernel(const float* __restr
 __global__ void __launch_bounds__(256) embed_in_kernel(const float* __restrict__ x, int ldx, int d_in,
                                                        const float* __restrict__ W0t, const float* __restrict__ b0,
                                                        const float* __restrict__ g, const float* __restrict__ b,
-                                                       __half* __restrict__ y, int ldy, int rows) {
+                                                       __half* __restrict__ y, int ldy, int rows,
+                                                       const int* __restrict__ rows_dev, const int* __restrict__ row_map) {
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
+  if (rows_dev) rows = min(rows, *rows_dev);
   for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
-    const float* xr = x + (size_t)row * ldx;
+    const float* xr = x + (size_t)(row_map ? row_map[row] : row) * ldx;      // compaction: gather the source token
     float v[24];
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
@@ -123,8 +127,10 @@ __global__ void __launch_bounds__(256) embed_in_kernel(const float* __restrict__
 __global__ void __launch_bounds__(256) ln_silu_head_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ g,
                                                            const float* __restrict__ b, const float* __restrict__ W,
                                                            const float* __restrict__ bias, float* __restrict__ out, int d_out,
-                                                           int rows) {
+                                                           int rows, const int* __restrict__ rows_dev,
+                                                           const int* __restrict__ row_map) {
   extern __shared__ float sW[];   // [d_out][768]
+  if (rows_dev) rows = min(rows, *rows_dev);
   for (int i = threadIdx.x; i < d_out * D / 4; i += blockDim.x)
     reinterpret_cast<float4*>(sW)[i] = __ldg(reinterpret_cast<const float4*>(W) + i);
   __syncthreads();
@@ -155,7 +161,7 @@ __global__ void __launch_bounds__(256) ln_silu_head_kernel(const float* __restri
       if ((o & 31) == lane) mine = acc + __ldg(bias + o);
       if ((o & 31) == 31 || o == d_out - 1) {
         const int o0 = o & ~31;
-        if (o0 + lane <= o) out[(size_t)row * d_out + o0 + lane] = mine;
+        if (o0 + lane <= o) out[(size_t)(row_map ? row_map[row] : row) * d_out + o0 + lane] = mine;   // compaction: scatter
       }
     }
   }
@@ -200,6 +206,58 @@ __global__ void mask_expand_kernel(const uint8_t* __restrict__ face_mask, uint8_
   if (i < BS * E) edge_mask[i] = face_mask[i / E];
 }
 
+// ---- mask-aware token compaction (padded tokens are never attended to and their outputs are
+// discarded downstream, sample.py:245,284, so dropping them is result-preserving for the valid tokens) ----
+// pass 1 (grid B): seq_len[b] = number of valid tokens of sample b
+__global__ void compact_count_kernel(const uint8_t* __restrict__ mask, int L, int* __restrict__ seq_len) {
+  const int b = blockIdx.x;
+  int n = 0;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) n += mask[(size_t)b * L + i] == 0;
+  n = (int)warp_sum((float)n);           // counts <= 8192 per warp: exact in fp32
+  __shared__ int part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = n;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += part[w];
+    seq_len[b] = t;
+  }
+}
+// pass 2 (one block): seq_row0 = exclusive prefix sum of seq_len, m_valid = total
+__global__ void compact_scan_kernel(const int* __restrict__ seq_len, int B, int* __restrict__ seq_row0, int* __restrict__ m_valid) {
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int b = 0; b < B; ++b) {
+      seq_row0[b] = acc;
+      acc += seq_len[b];
+    }
+    *m_valid = acc;
+  }
+}
+// pass 3 (grid B, one warp): row_map[seq_row0[b] + rank] = b * L + token for the valid tokens in order
+__global__ void compact_map_kernel(const uint8_t* __restrict__ mask, int L, const int* __restrict__ seq_row0,
+                                   int* __restrict__ row_map) {
+  const int b = blockIdx.x, lane = threadIdx.x;
+  int base = seq_row0[b];
+  for (int i0 = 0; i0 < L; i0 += 32) {
+    const int i = i0 + lane;
+    const bool ok = i < L && mask[(size_t)b * L + i] == 0;
+    const uint32_t bal = __ballot_sync(0xffffffffu, ok);
+    if (ok) row_map[base + __popc(bal & ((1u << lane) - 1))] = b * L + i;
+    base += __popc(bal);
+  }
+}
+
+// zero `nrows` rows of a fp16 matrix starting at row *row0_dev (clipped to max_rows): the variable-length attention reads up
+// to 127 rows past the last valid token (masked keys, p = 0) and 0 x NaN from stale memory must not reach the accumulator
+__global__ void zero_rows_kernel(__half* __restrict__ y, int ld, int cols, const int* __restrict__ row0_dev, int nrows, int max_rows) {
+  const int r0 = *row0_dev;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nrows * (cols / 8); i += gridDim.x * blockDim.x) {
+    const int r = r0 + i / (cols / 8), c = (i % (cols / 8)) * 8;
+    if (r < max_rows) *reinterpret_cast<uint4*>(y + (size_t)r * ld + c) = make_uint4(0, 0, 0, 0);
+  }
+}
+
 inline int row_grid(int rows, int wpb) {
   const int want = (rows + wpb - 1) / wpb;
   const int cap = num_sms() * 8;
@@ -209,28 +267,42 @@ inline int row_grid(int rows, int wpb) {
 }  // namespace
 
 int launch_layernorm_f16(cudaStream_t st, const float* x, int ldx, const float* g, const float* b, __half* y, int ldy,
-                         int rows, int act, int lo_offset) {
+                         int rows, int act, int lo_offset, const int* rows_dev) {
   BG_REQUIRE(rows > 0 && ldx % 4 == 0 && ldy % 4 == 0 && lo_offset % 4 == 0, "layernorm: bad shape");
-  layernorm_f16_kernel<<<row_grid(rows, 8), 256, 0, st>>>(x, ldx, g, b, y, ldy, rows, act, lo_offset);
+  layernorm_f16_kernel<<<row_grid(rows, 8), 256, 0, st>>>(x, ldx, g, b, y, ldy, rows, act, lo_offset, rows_dev);
   return check_launch("layernorm_f16_kernel launch");
 }
 
 int launch_embed_in(cudaStream_t st, const float* x, int ldx, int d_in, const float* W0t, const float* b0, const float* g,
-                    const float* b, __half* y, int ldy, int rows) {
+                    const float* b, __half* y, int ldy, int rows, const int* rows_dev, const int* row_map) {
   BG_REQUIRE(rows > 0 && d_in > 0 && ldy % 4 == 0, "embed_in: bad shape");
-  embed_in_kernel<<<row_grid(rows, 8), 256, 0, st>>>(x, ldx, d_in, W0t, b0, g, b, y, ldy, rows);
+  embed_in_kernel<<<row_grid(rows, 8), 256, 0, st>>>(x, ldx, d_in, W0t, b0, g, b, y, ldy, rows, rows_dev, row_map);
   return check_launch("embed_in_kernel launch");
 }
 
 int launch_ln_silu_head(cudaStream_t st, const float* x, int ldx, const float* g, const float* b, const float* W,
-                        const float* bias, float* out, int d_out, int rows) {
+                        const float* bias, float* out, int d_out, int rows, const int* rows_dev, const int* row_map) {
   BG_REQUIRE(rows > 0 && d_out > 0 && d_out <= 64 && ldx % 4 == 0, "ln_silu_head: bad shape");
   const int smem = d_out * D * 4;
   BG_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&ln_silu_head_kernel), 64 * D * 4));
   const int want = (rows + 7) / 8;
   const int cap = num_sms() * 2;
-  ln_silu_head_kernel<<<want < cap ? want : cap, 256, smem, st>>>(x, ldx, g, b, W, bias, out, d_out, rows);
+  ln_silu_head_kernel<<<want < cap ? want : cap, 256, smem, st>>>(x, ldx, g, b, W, bias, out, d_out, rows, rows_dev, row_map);
   return check_launch("ln_silu_head_kernel launch");
+}
+
+int launch_compact(cudaStream_t st, const uint8_t* mask, int B, int L, int* seq_len, int* seq_row0, int* m_valid, int* row_map) {
+  BG_REQUIRE(mask && B > 0 && L > 0 && seq_len && seq_row0 && m_valid && row_map, "compact: bad arguments");
+  compact_count_kernel<<<B, 256, 0, st>>>(mask, L, seq_len);
+  compact_scan_kernel<<<1, 32, 0, st>>>(seq_len, B, seq_row0, m_valid);
+  compact_map_kernel<<<B, 32, 0, st>>>(mask, L, seq_row0, row_map);
+  return check_launch("compact kernels launch");
+}
+
+int launch_zero_rows_f16(cudaStream_t st, __half* y, int ld, int cols, const int* row0_dev, int nrows, int max_rows) {
+  BG_REQUIRE(y && row0_dev && cols % 8 == 0 && ld % 8 == 0 && nrows > 0, "zero_rows: bad arguments");
+  zero_rows_kernel<<<64, 256, 0, st>>>(y, ld, cols, row0_dev, nrows, max_rows);
+  return check_launch("zero_rows_kernel launch");
 }
 
 int launch_cond(cudaStream_t st, const float* time_table, const int64_t* t, int n_t, const float* class_table,

@@ -42,7 +42,8 @@ struct Cfg {
 
 template <int BN>
 __global__ void __launch_bounds__(384, 1)
-gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p_in) {
+  const GemmParams p = gemm_resolve(p_in);
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -184,20 +185,30 @@ int launch_gemm_f16(cudaStream_t st, const __half* A, int lda, const __half* W, 
   BG_REQUIRE(ep.resid == nullptr || (ep.ldr % 4 == 0 && !ep.out_f16 ? true : ep.ldr % 4 == 0), "gemm: resid pitch");
   BG_REQUIRE(ep.rowvec == nullptr || (ep.rows_per_vec > 0 && ep.ldv % 4 == 0), "gemm: rowvec");
   BG_REQUIRE(!ep.out_f16 || (ep.resid == nullptr && ep.rowvec == nullptr), "gemm: fp16 output supports bias / ReLU only");
-  const int bn = (N % 256 == 0) ? 256 : 128;
-  static int two_cta = -1;              // CTA-pair kernel (gemm2.cu) for N % 256 == 0; BG_GEMM_2CTA=0 selects the 1-CTA kernel
+  static int two_cta = -1, small_m = -1;   // environment knobs, read once per process
   if (two_cta < 0) {
-    const char* e = getenv("BG_GEMM_2CTA");
+    const char* e = getenv("BG_GEMM_2CTA");   // 0: never use the CTA-pair kernel (gemm2.cu)
     two_cta = e ? atoi(e) : 1;
+    e = getenv("BG_GEMM_SMALLM");             // 0: no small-problem tile selection
+    small_m = e ? atoi(e) : 1;
   }
-  const bool use2 = two_cta && bn == 256;
+  // Tile selection.  Large problems: 256 x 256 tiles on CTA pairs (half the weight traffic per CTA).  When that gives fewer
+  // tiles than there are CTA pairs (the surface stages: M = B x S of a few thousand rows), most SMs idle and the kernel time
+  // is the latency of ONE tile's serial main loop -- 128 x 128 tiles on single CTAs give 4x as many tiles with a 4x shorter
+  // main loop each.
+  int bn = (N % 256 == 0) ? 256 : 128;
+  bool use2 = two_cta && bn == 256;
+  if (small_m && bn == 256 && (long long)((M + 255) / 256) * (N / 256) < num_sms() / 2) {
+    bn = 128;
+    use2 = false;
+  }
   CUtensorMap tmA, tmB;
   const int a_cols = ep.a_kwrap > 0 ? ep.a_kwrap : K;
   BG_REQUIRE(ep.a_kwrap == 0 || (ep.a_kwrap % BK == 0 && ep.a_kwrap <= K), "gemm: a_kwrap must be a multiple of 64");
   BG_TRY(make_tmap_2d_f16(&tmA, A, (uint64_t)M, (uint64_t)a_cols, (uint64_t)lda, BM));
   BG_TRY(make_tmap_2d_f16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, use2 ? 128u : (uint32_t)bn));
   GemmParams p;
-  p.M = M; p.N = N; p.K = K; p.a_kwrap = ep.a_kwrap;
+  p.M = M; p.N = N; p.K = K; p.a_kwrap = ep.a_kwrap; p.m_dev = ep.m_dev; p.row_map = ep.row_map;
   p.out = ep.out; p.ldo = ep.ldo; p.out_f16 = ep.out_f16; p.relu = ep.relu;
   p.bias = ep.bias; p.resid = ep.resid; p.ldr = ep.ldr;
   p.rowvec = ep.rowvec; p.rows_per_vec = ep.rows_per_vec; p.ldv = ep.ldv;

@@ -98,8 +98,9 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
 
 template <int RES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
-gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p,
+gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p_in,
                  const __grid_constant__ EpiMaps<RES> em) {
+  const GemmParams p = gemm_resolve(p_in);
   constexpr int STAGES = RES ? X_STAGES : NSTAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));

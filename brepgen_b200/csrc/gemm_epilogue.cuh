@@ -18,7 +18,16 @@ struct GemmParams {
   const float* rowvec;
   int rows_per_vec;
   int ldv;
+  const int* m_dev;     // optional device int: the kernels work on min(M, *m_dev) rows (token compaction)
+  const int* row_map;   // optional: rowvec row = row_map[row] / rows_per_vec
 };
+
+// the kernels' working copy of the parameters with the row count resolved on the device
+__device__ __forceinline__ GemmParams gemm_resolve(const GemmParams& p) {
+  GemmParams q = p;
+  if (p.m_dev) q.M = min(p.M, *p.m_dev);
+  return q;
+}
 
 
 constexpr int GEMM_XPOSE_PITCH = 33;   // floats; +1 keeps both access patterns of the 32x32 staging tile conflict-free
@@ -53,7 +62,8 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
 #pragma unroll
           for (int rr = 0; rr < 32; ++rr) {
             const int row = row0 + rr;
-            if (row < p.M) add[rr] += __ldg(p.rowvec + (size_t)(row / p.rows_per_vec) * p.ldv + col);
+            if (row < p.M)
+              add[rr] += __ldg(p.rowvec + (size_t)((p.row_map ? p.row_map[row] : row) / p.rows_per_vec) * p.ldv + col);
           }
         }
         uint32_t r[32];

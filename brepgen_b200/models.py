@@ -69,6 +69,8 @@ class _Denoiser(nn.Module):
             _register_tree(self, key, _default_init(key, shape))
         # 0 / 1 / 2, see include/brepgen_b200.h (bg_denoiser_create); 1 meets the 1e-3 parity bar with margin
         self.precision = int(os.environ.get("BREPGEN_B200_PRECISION", "1"))
+        # mask-aware token compaction (BgDenoiserArgs.compact): on whenever a mask is passed; 0 = dense layout with masking only
+        self.compact = int(os.environ.get("BREPGEN_B200_COMPACT", "1"))
         self._handle = None
         self._packed_sig = None
         self._dirty = True           # parameters may have changed since the last pack (set by load_state_dict / .to() / ...)
@@ -210,7 +212,8 @@ class _Denoiser(nn.Module):
                 class_label = None
             out = torch.empty_like(x)
             a = _ffi.BgDenoiserArgs(B, S, E, x.data_ptr(), ts.data_ptr(), ts.numel(), _ffi.ptr(surfPos), _ffi.ptr(surfZ),
-                                    _ffi.ptr(edgePos), _ffi.ptr(mask), _ffi.ptr(class_label), out.data_ptr())
+                                    _ffi.ptr(edgePos), _ffi.ptr(mask), _ffi.ptr(class_label), out.data_ptr(),
+                                    int(self.compact))
             ws = self._workspace(B, S, E, dev)
             _ffi.check(_ffi.lib().bg_denoiser_forward(self._handle, C.byref(a), ws.data_ptr(), ws.numel(),
                                                      _ffi.current_stream()), "bg_denoiser_forward")

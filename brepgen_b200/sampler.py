@@ -38,6 +38,8 @@ class CascadeConfig:
     schedule: str = "reference"          # "reference" | "ddpm"
     ddpm_steps: int = 1000               # per stage, schedule == "ddpm"
     dense_masks: bool = False            # True: skip dedup, every slot valid (the dense-FLOP benchmark mode)
+    ragged_masks: bool = False           # benchmark only: synthetic masks shaped like a trained model's output (random-init
+                                         # weights never produce duplicates): 1/8..1/2 of the faces valid, 3..E/3 edges each
     seed: int = 0
     decode: bool = True
     graph: str = "auto"                  # "on" | "off" | "auto": capture each DDPM loop (advance, forward, fused step) in a CUDA
@@ -257,7 +259,11 @@ class Cascade:
             surfPos = surfPos.repeat(1, 2, 1)
 
         # STEP 1-2 duplicate faces (sample.py:159-183)
-        if cfg.dense_masks:
+        mask_gen = torch.Generator().manual_seed(cfg.seed + 12345)
+        if cfg.ragged_masks:
+            nv = torch.randint(max(1, S // 8), max(2, S // 2) + 1, (B,), generator=mask_gen)
+            surfMask = (torch.arange(S)[None, :] >= nv[:, None]).to(dev)
+        elif cfg.dense_masks:
             surfMask = torch.zeros(B, S, dtype=torch.bool, device=dev)
         else:
             surfPos, surfMask = dedup_surfaces(surfPos, cfg.bbox_threshold)
@@ -275,7 +281,10 @@ class Cascade:
                               noise_fn=nf("edgePos"), name="edgePos")
 
         # STEP 2-2 duplicate edges per face (sample.py:242-261)
-        if cfg.dense_masks:
+        if cfg.ragged_masks:
+            ne = torch.randint(min(3, E), max(min(3, E), E // 3) + 1, (B, S), generator=mask_gen)
+            edgeM = (torch.arange(E)[None, None, :] >= ne[..., None]).to(dev) | surfMask[..., None]
+        elif cfg.dense_masks:
             edgeM = torch.zeros(B, S, E, dtype=torch.bool, device=dev)
         else:
             edgeM = dedup_edges(edgePos, surfMask, cfg.bbox_threshold)

@@ -76,6 +76,12 @@ typedef struct {
   const uint8_t* mask;         /* kind 1,2: (B,S) face mask; kind 3: (B,S,E) edge mask; nonzero = padded; may be NULL */
   const int64_t* class_label;  /* (B,1) when created with use_cf, else NULL */
   float* out;                  /* prediction, same shape as x, fp32 */
+  int compact;                 /* != 0 and a mask is given: mask-aware token compaction -- the valid tokens of every sample
+                                * are gathered before the encoder (embeds, LayerNorms and GEMMs run on sum(valid) rows,
+                                * attention on ceil(valid / 128) tiles per sample) and the head scatters back; outputs of
+                                * padded tokens are 0.  Result-preserving for the valid tokens: padded keys are never
+                                * attended to (network.py:1268,1387-1390) and padded outputs are discarded downstream
+                                * (sample.py:245,284). */
 } BgDenoiserArgs;
 
 size_t bg_denoiser_workspace_bytes(const BgDenoiser* m, int B, int S, int E);
