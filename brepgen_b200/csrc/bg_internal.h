@@ -66,6 +66,7 @@ struct GemmEpilogue {
   int rows_per_vec = 1;
   int ldv = 0;
   int a_kwrap = 0;               // >0: A has a_kwrap columns and is reused cyclically along K (split-weight GEMM)
+  int n_short = 0, k_short = 0;  // column tiles below n_short (a multiple of 256) use only the first k_short columns of K
   const int* m_dev = nullptr;    // optional device int: only min(M, *m_dev) rows are computed (token compaction)
   const int* row_map = nullptr;  // optional: rowvec is indexed with row_map[row] / rows_per_vec instead of row / rows_per_vec
 };

@@ -44,10 +44,11 @@ const KindDef KINDS[4] = {
 };
 
 struct LayerW {
-  // [N][k*] fp16; k* = K (single) or 2K ([W_hi | W_lo], split-weight GEMM).  in_proj is packed as two operands: the
-  // q|k rows (their rounding error only perturbs the softmax logits: 1.5e-5 of the output) and the v rows (4.8e-4, split)
-  __half *wqk, *wv, *wo, *w1, *w2;
-  int kqk, kv, ko, k1, k2;
+  // [N][k*] fp16; k* = K (single) or 2K ([W_hi | W_lo], split-weight GEMM).  in_proj is ONE operand [2304][kqkv]: at
+  // precision 1 only the v rows (>= qk_rows) carry a lo half (their rounding error is 4.8e-4 of the output; the q|k rows only
+  // perturb the softmax logits: 1.5e-5) and the GEMM stops at K = 768 for the q|k column tiles (GemmEpilogue::n_short)
+  __half *wqkv, *wo, *w1, *w2;
+  int kqkv, qk_short, ko, k1, k2;
   float *bqkv, *bo, *b1, *b2, *ln1g, *ln1b, *ln2g, *ln2b;
 };
 
@@ -222,8 +223,23 @@ int pack(BgDenoiser* m, Packer& pk, const float* sincos) {
     const std::string p = "net.layers." + std::to_string(i) + ".";
     LayerW& L = m->layer[i];
     const bool s_attn = m->precision >= 1, s_ff = m->precision >= 2;
-    L.wqk = pk.pack_weight(p + "self_attn.in_proj_weight", 2 * D, D, s_ff, &L.kqk, 0, 3 * D);
-    L.wv = pk.pack_weight(p + "self_attn.in_proj_weight", D, D, s_attn, &L.kv, 2 * D, 3 * D);
+    if (s_attn && !s_ff) {      // precision 1: [q|k rows: W_hi, unused] / [v rows: W_hi | W_lo]
+      const float* src = pk.find(p + "self_attn.in_proj_weight", (int64_t)3 * D * D);
+      L.kqkv = 2 * D;
+      L.qk_short = 1;
+      L.wqkv = pk.take<__half>((size_t)3 * D * 2 * D);
+      if (!pk.dry && src && !pk.err) {
+        pk.err = check_cuda(cudaMemsetAsync(L.wqkv, 0, (size_t)3 * D * 2 * D * sizeof(__half), pk.st), "memset");
+        const unsigned bqk = (unsigned)(((size_t)2 * D * D + 255) / 256), bv = (unsigned)(((size_t)D * D + 255) / 256);
+        pack_split_kernel<<<bqk, 256, 0, pk.st>>>(src, L.wqkv, 2 * D, D, 2 * D, 0, 0);
+        pack_split_kernel<<<bv, 256, 0, pk.st>>>(src + (size_t)2 * D * D, L.wqkv + (size_t)2 * D * 2 * D, D, D, 2 * D, 0, 0);
+        pack_split_kernel<<<bv, 256, 0, pk.st>>>(src + (size_t)2 * D * D, L.wqkv + (size_t)2 * D * 2 * D, D, D, 2 * D, D, 1);
+        if (!pk.err) pk.err = check_launch("pack in_proj");
+      }
+    } else {
+      L.qk_short = 0;
+      L.wqkv = pk.pack_weight(p + "self_attn.in_proj_weight", 3 * D, D, s_ff, &L.kqkv);
+    }
     L.bqkv = pk.copy_f32(p + "self_attn.in_proj_bias", 3 * D);
     L.wo = pk.pack_weight(p + "self_attn.out_proj.weight", D, D, s_attn, &L.ko);
     L.bo = pk.copy_f32(p + "self_attn.out_proj.bias", D);
@@ -500,11 +516,10 @@ int bg_denoiser_forward(BgDenoiser* m, const BgDenoiserArgs* a, void* workspace,
       GemmEpilogue ep;
       ep.m_dev = m_dev;
       ep.out = w.QKV; ep.ldo = 3 * D; ep.out_f16 = 1; ep.bias = Lw.bqkv;
-      ep.a_kwrap = Lw.kqk > D ? D : 0;
-      BG_TRY(launch_gemm_f16(st, w.Xn, D, Lw.wqk, Lw.kqk, M, 2 * D, Lw.kqk, ep));     // q | k
-      ep.out = w.QKV + 2 * D; ep.bias = Lw.bqkv + 2 * D;
-      ep.a_kwrap = Lw.kv > D ? D : 0;
-      BG_TRY(launch_gemm_f16(st, w.Xn, D, Lw.wv, Lw.kv, M, D, Lw.kv, ep));            // v
+      // one GEMM for q | k | v (Xn is read once): at precision 1 the q|k column tiles stop after the hi half of K
+      ep.a_kwrap = Lw.kqkv > D ? D : 0;
+      if (Lw.qk_short) { ep.n_short = 2 * D; ep.k_short = D; }
+      BG_TRY(launch_gemm_f16(st, w.Xn, D, Lw.wqkv, Lw.kqkv, M, 3 * D, Lw.kqkv, ep));
     }
     {
       AttnArgs at;

@@ -88,7 +88,8 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_blk = tile / num_n, n_blk = tile % num_n;
-        for (int kb = 0; kb < num_k; ++kb) {
+        const int nk = (n_blk * BN < p.n_short) ? p.k_short / BK : num_k;
+        for (int kb = 0; kb < nk; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sA = smem + stage * C::STAGE_BYTES;
           uint8_t* sB = sA + C::A_BYTES;
@@ -111,7 +112,8 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         mbar_wait(&tempty[acc], accphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_k; ++kb) {
+        const int nk = ((tile % num_n) * BN < p.n_short) ? p.k_short / BK : num_k;
+        for (int kb = 0; kb < nk; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * C::STAGE_BYTES);
@@ -209,6 +211,9 @@ int launch_gemm_f16(cudaStream_t st, const __half* A, int lda, const __half* W, 
   BG_TRY(make_tmap_2d_f16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, use2 ? 128u : (uint32_t)bn));
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.a_kwrap = ep.a_kwrap; p.m_dev = ep.m_dev; p.row_map = ep.row_map;
+  p.n_short = ep.n_short; p.k_short = ep.k_short;
+  BG_REQUIRE(ep.n_short == 0 || (ep.n_short % 256 == 0 && ep.k_short % BK == 0 && ep.k_short > 0 && ep.k_short <= K),
+             "gemm: n_short must be a multiple of 256 and k_short a multiple of 64");
   p.out = ep.out; p.ldo = ep.ldo; p.out_f16 = ep.out_f16; p.relu = ep.relu;
   p.bias = ep.bias; p.resid = ep.resid; p.ldr = ep.ldr;
   p.rowvec = ep.rowvec; p.rows_per_vec = ep.rows_per_vec; p.ldv = ep.ldv;

@@ -156,7 +156,8 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         const int m_blk = tile / num_n, n_blk = tile % num_n;
-        for (int kb = 0; kb < num_k; ++kb) {
+        const int nk = (n_blk * BN < p.n_short) ? p.k_short / BK : num_k;
+        for (int kb = 0; kb < nk; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sA = smem + stage * STAGE_BYTES;
           uint8_t* sB = sA + A_BYTES;
@@ -180,7 +181,8 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(&tempty[acc], accphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_k; ++kb) {
+        const int nk = ((tile % num_n) * BN < p.n_short) ? p.k_short / BK : num_k;
+        for (int kb = 0; kb < nk; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);

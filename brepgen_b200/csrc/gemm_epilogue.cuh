@@ -18,6 +18,7 @@ struct GemmParams {
   const float* rowvec;
   int rows_per_vec;
   int ldv;
+  int n_short, k_short; // column tiles with n0 < n_short run only k_short / 64 k-blocks (partly split weight matrix)
   const int* m_dev;     // optional device int: the kernels work on min(M, *m_dev) rows (token compaction)
   const int* row_map;   // optional: rowvec row = row_map[row] / rows_per_vec
 };

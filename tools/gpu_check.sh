@@ -1,9 +1,8 @@
 #!/bin/bash
-# one gpurun call: GPU test suite, then compaction / small-M timings
 set -x
-timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
+timeout 900 python -m pytest tests/test_gpu_denoisers.py tests/test_gpu_l4000.py tests/test_gpu_compaction.py tests/test_gpu_ops.py -x -q 2>&1 | tail -5
+timeout 120 python tools/profile_forward.py --kind edgepos --batch 64 --iters 3 --time
 timeout 120 python tools/profile_forward.py --kind surfpos --batch 64 --surfaces 30 --iters 50 --time
-BG_GEMM_SMALLM=0 timeout 120 python tools/profile_forward.py --kind surfpos --batch 64 --surfaces 30 --iters 50 --time
-timeout 600 python bench.py --batch 32 --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --masks ragged --compact 1 > gpurun_out/bench_ragged_c1.json 2> gpurun_out/bench_ragged_c1.err; tail -c 1200 gpurun_out/bench_ragged_c1.json
-timeout 600 python bench.py --batch 32 --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --masks ragged --compact 0 > gpurun_out/bench_ragged_c0.json 2> gpurun_out/bench_ragged_c0.err; tail -c 1200 gpurun_out/bench_ragged_c0.json
-timeout 600 python bench.py --batch 32 --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/bench_dense_b32.json 2> gpurun_out/bench_dense_b32.err; tail -c 1200 gpurun_out/bench_dense_b32.json
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_kernel -s 5 -c 1 -o gpurun_out/r02_attn_b256 -f env B=256 python tools/attn_check.py > gpurun_out/r02_attn_ncu.out 2>&1
+timeout 600 python bench.py --workload surfpos > gpurun_out/bench_surfpos2.json 2> gpurun_out/bench_surfpos2.err; tail -c 600 gpurun_out/bench_surfpos2.json
+timeout 1500 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; tail -c 3000 gpurun_out/bench_default.json
