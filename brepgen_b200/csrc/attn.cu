@@ -362,7 +362,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const float2 a = ffma2(make_float2(s[16 * g + 2 * q], s[16 * g + 2 * q + 1]), c2, nmc2);
-          e[q] = ((PM >> (q & 3)) & 1) ? exp2_poly2(a) : make_float2(ex2(a.x), ex2(a.y));
+          // PM: bits 0-3 = pattern of the even 16-key groups, bits 4-7 = of the odd ones (0 = same as even)
+          e[q] = ((((g & 1) && (PM >> 4)) ? (PM >> 4) : PM) >> (q & 3)) & 1 ? exp2_poly2(a) : make_float2(ex2(a.x), ex2(a.y));
         }
       };
       auto drain_group = [&](int g, const float2 (&e)[8]) {
@@ -510,7 +511,7 @@ int launch_attention(cudaStream_t st, const AttnArgs& a) {
   p.scale_log2 = 1.4426950408889634f / 8.0f;
   static int poly = -1, ptmem = 1, pingpong = 1;   // environment knobs, read once per process
   if (poly < 0) {
-    const char* e = getenv("BG_ATTN_POLY");   // share of the exponentials on the FMA pipe: 0 | 1 (25 %, default) | 2 (50 %)
+    const char* e = getenv("BG_ATTN_POLY");   // share of the exponentials on the FMA pipe: 0 | 1 (25 %, default) | 2 (50 %) | 3 (37.5 %)
     poly = e ? atoi(e) : 1;
     e = getenv("BG_ATTN_PT");                 // 0: P through shared memory (the round-1 path, kept as the A/B reference)
     ptmem = e ? atoi(e) : 1;
@@ -523,6 +524,7 @@ int launch_attention(cudaStream_t st, const AttnArgs& a) {
   if (ptmem) {
     if (poly == 0) return launch_nt<2, 0x0, 1, 1>(st, tm, p);
     if (poly == 2) return launch_nt<2, 0xA, 1, 1>(st, tm, p);
+    if (poly == 3) return launch_nt<2, 0xA8, 1, 1>(st, tm, p);    // 37.5 %: 25 % in even, 50 % in odd 16-key groups
     return launch_nt<2, 0x8, 1, 1>(st, tm, p);
   }
   if (poly == 0) return launch_nt<2, 0x0, 0, 1>(st, tm, p);

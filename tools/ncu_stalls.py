@@ -30,7 +30,7 @@ n = lambda r, k: int(r[ix[k]] or 0)
 tot = sum(n(r, "# Samples") for r in data)
 ops = [op(r[ix["Source"]]) for r in data]
 first = next(i for i, o in enumerate(ops) if o.startswith("LDTM")) - 40
-last = max(i for i, o in enumerate(ops) if o.startswith("MEMBAR")) + 12
+last = max(i for i, o in enumerate(ops) if o.startswith(("MEMBAR", "STTM"))) + 12     # end of the key-block loop body
 loop = data[first:last]
 ls = sum(n(r, "# Samples") for r in loop)
 print(f"\nWarp-state samples: {tot} in the kernel, {ls} ({100 * ls / tot:.1f} %) inside the softmax key-block loop "
