@@ -12,6 +12,7 @@ instantiates is supported (block_out_channels [128,256,512,512] / [128,256,512],
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 import torch.nn as nn
@@ -45,6 +46,8 @@ class _VaeModule(nn.Module):
             else:
                 _register_tree(self, key, torch.zeros(shape) if len(shape) == 1 else torch.randn(shape) * 0.02)
         self._handle, self._sig, self._ws = None, None, None
+        self._graphs = {}
+        self.use_graph = os.environ.get("BREPGEN_B200_VAE_GRAPH", "1") != "0"   # replay one captured chunk per chunk
 
     def _release(self):
         if self._handle is not None:
@@ -74,6 +77,7 @@ class _VaeModule(nn.Module):
         _ffi.check(_ffi.lib().bg_vae_create(self.kind, arr, len(sd), _ffi.current_stream(), C.byref(out)), "bg_vae_create")
         torch.cuda.current_stream().synchronize()
         self._handle, self._sig = out, sig
+        self._graphs = {}
 
     def forward(self, z: torch.Tensor) -> torch.Tensor:
         want_dim = 4 if self.kind in (0, 2) else 3       # surface VAEs: (N,3,H,W); edge VAEs: (N,3,L)
@@ -97,11 +101,39 @@ class _VaeModule(nn.Module):
             need = _ffi.lib().bg_vae_workspace_bytes(self._handle, step)
             if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
                 self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
-            for lo in range(0, N, step):
+                self._graphs = {}            # captured chunks point into the old workspace
+            fn = _ffi.lib().bg_vae_encode if encode else _ffi.lib().bg_vae_decode_hw
+            what = "bg_vae_encode" if encode else "bg_vae_decode"
+
+            def run(zp, n, op):
+                _ffi.check(fn(self._handle, zp, n, hw, op, self._ws.data_ptr(), self._ws.numel(), _ffi.current_stream()), what)
+
+            full = N // step
+            use_graph = self.use_graph and full >= 3 and not torch.cuda.is_current_stream_capturing()
+            if use_graph:
+                # A chunk is ~350 stream-ordered launches; with dozens of chunks per call (25 600 faces, 1 M edges at
+                # B = 256) the host side dominates and, with 8 ranks on one host, contends.  One chunk is captured in a CUDA
+                # graph over static staging buffers and replayed per chunk (two device copies around each replay).
+                key = (self._handle.value, step, hw, tuple(z.shape[1:]), dev.index)
+                g = self._graphs.get(key)
+                if g is None:
+                    zs, os_ = torch.empty_like(z[:step]), torch.empty_like(out[:step])
+                    run(z[:step].data_ptr(), step, os_.data_ptr())           # warm-up outside the capture
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        run(zs.data_ptr(), step, os_.data_ptr())
+                    g = self._graphs[key] = (graph, zs, os_)
+                graph, zs, os_ = g
+                for c in range(full):
+                    zs.copy_(z[c * step:(c + 1) * step])
+                    graph.replay()
+                    out[c * step:(c + 1) * step].copy_(os_)
+                lo0 = full * step
+            else:
+                lo0 = 0
+            for lo in range(lo0, N, step):
                 n = min(step, N - lo)
-                fn = _ffi.lib().bg_vae_encode if encode else _ffi.lib().bg_vae_decode_hw
-                _ffi.check(fn(self._handle, z[lo:lo + n].data_ptr(), n, hw, out[lo:lo + n].data_ptr(), self._ws.data_ptr(),
-                              self._ws.numel(), _ffi.current_stream()), "bg_vae_encode" if encode else "bg_vae_decode")
+                run(z[lo:lo + n].data_ptr(), n, out[lo:lo + n].data_ptr())
         return out
 
 
@@ -165,3 +197,23 @@ def build_synthetic_decoders(device, seed: int = 2):
     s.load_state_dict(synth_state_dict(surf_decoder_spec(), seed), strict=False)
     e.load_state_dict(synth_state_dict(edge_decoder_spec(), seed), strict=False)
     return s.to(device).eval(), e.to(device).eval()
+
+
+# ------------------------------------------------------------------------------------------------ training-side latent pass
+def encode_surface_latents(surf_vae, surfPnt: torch.Tensor, z_scaled: float = 1.0) -> torch.Tensor:
+    """The frozen-encoder pass that feeds LDM training (trainer.py:518-524, :704-709, :918-927): surfPnt (B, S, 32, 32, 3)
+    -> surfZ (B, S, 48) = flattened 4 x 4 x 3 latent of every face (position-major, channel-minor) times z_scaled."""
+    bsz = surfPnt.shape[0]
+    surf_uv = surfPnt.flatten(0, 1).permute(0, 3, 1, 2)
+    surf_z = surf_vae(surf_uv.contiguous())
+    surf_z = surf_z.unflatten(0, (bsz, -1)).flatten(-2, -1).permute(0, 1, 3, 2)
+    return surf_z.flatten(-2, -1) * z_scaled
+
+
+def encode_edge_latents(edge_vae, edgePnt: torch.Tensor, z_scaled: float = 1.0) -> torch.Tensor:
+    """trainer.py:922-928: edgePnt (B, S, E, 32, 3) -> edgeZ (B, S, E, 12) = flattened 4 x 3 latent of every edge times z_scaled"""
+    bsz, _, max_edge = edgePnt.shape[:3]
+    edge_u = edgePnt.flatten(0, 1).flatten(0, 1).permute(0, 2, 1)
+    edge_z = edge_vae(edge_u.contiguous())
+    edge_z = edge_z.unflatten(0, (-1, max_edge)).unflatten(0, (bsz, -1)).permute(0, 1, 2, 4, 3)
+    return edge_z.flatten(-2, -1) * z_scaled

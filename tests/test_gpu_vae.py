@@ -126,3 +126,51 @@ def test_config1_roundtrip():
     e2 = rel_l2(ye, refe)
     print(f"config-1 round trip: surface 16x16 rel_l2={e1:.3e}  edge rel_l2={e2:.3e}")
     assert e1 < 1e-3 and e2 < 1e-3
+
+
+def test_training_side_latent_pass():
+    """the frozen-encoder pass that feeds LDM training (trainer.py:518-524, 918-928): surfPnt (B,S,32,32,3) -> surfZ (B,S,48),
+    edgePnt (B,S,E,32,3) -> edgeZ (B,S,E,12), with the reference's reshapes around the drop-in encoders; against the same
+    statements around the oracle encoders"""
+    from brepgen_b200.spec import edge_encoder_spec, surf_encoder_spec
+    from brepgen_b200.vae import (AutoencoderKL1DFastEncode, AutoencoderKLFastEncode, encode_edge_latents,
+                                  encode_surface_latents)
+    g = torch.Generator().manual_seed(4)
+    sd_s, sd_e = synth_state_dict(surf_encoder_spec(), 5), synth_state_dict(edge_encoder_spec(), 5)
+    es, ee = AutoencoderKLFastEncode(), AutoencoderKL1DFastEncode()
+    es.load_state_dict(sd_s, strict=False)
+    ee.load_state_dict(sd_e, strict=False)
+    es, ee = es.cuda().eval(), ee.cuda().eval()
+    B, S, E, zs = 2, 3, 4, 1.0
+    surfPnt = torch.rand(B, S, 32, 32, 3, generator=g) * 2 - 1
+    edgePnt = torch.rand(B, S, E, 32, 3, generator=g) * 2 - 1
+    with torch.no_grad():
+        surfZ = encode_surface_latents(es, surfPnt.cuda(), zs).cpu()
+        edgeZ = encode_edge_latents(ee, edgePnt.cuda(), zs).cpu()
+        # the reference's statements (trainer.py:919-928) around the oracle encoders
+        sz = V.surf_encode(sd_s, surfPnt.flatten(0, 1).permute(0, 3, 1, 2))
+        sz = sz.unflatten(0, (B, -1)).flatten(-2, -1).permute(0, 1, 3, 2).flatten(-2, -1) * zs
+        ez = V.edge_encode(sd_e, edgePnt.flatten(0, 1).flatten(0, 1).permute(0, 2, 1))
+        ez = ez.unflatten(0, (-1, E)).unflatten(0, (B, -1)).permute(0, 1, 2, 4, 3).flatten(-2, -1) * zs
+    assert surfZ.shape == (B, S, 48) and edgeZ.shape == (B, S, E, 12)
+    e1, e2 = rel_l2(surfZ, sz), rel_l2(edgeZ, ez)
+    print(f"training-side latent pass: surfZ rel_l2={e1:.3e} edgeZ rel_l2={e2:.3e}")
+    assert e1 < 1e-3 and e2 < 1e-3
+
+
+def test_decoders_graph_replay_equals_eager():
+    """many chunks per call: one chunk is captured in a CUDA graph and replayed (vae.py); results identical to eager chunks"""
+    from brepgen_b200.vae import build_synthetic_decoders
+    sv, ev = build_synthetic_decoders(torch.device("cuda"))
+    sv.chunk, ev.chunk = 3, 8
+    zs = torch.randn(14, 3, 4, 4, generator=torch.Generator().manual_seed(1)).cuda()     # 4 full chunks + 2
+    ze = torch.randn(43, 3, 4, generator=torch.Generator().manual_seed(2)).cuda()        # 5 full chunks + 3
+    with torch.no_grad():
+        sv.use_graph = ev.use_graph = False
+        a_s, a_e = sv(zs), ev(ze)
+        sv.use_graph = ev.use_graph = True
+        b_s, b_e = sv(zs), ev(ze)
+        c_s = sv(zs)                                  # second call re-uses the captured chunk
+    torch.cuda.synchronize()
+    assert len(sv._graphs) == 1 and len(ev._graphs) == 1
+    assert torch.equal(a_s, b_s) and torch.equal(a_e, b_e) and torch.equal(b_s, c_s)
