@@ -228,3 +228,35 @@ def joint_optimize(surf_ncs, edge_ncs, surfPos, unique_vertices, EdgeVertexAdj, 
                                       max(len(a) for a in FaceEdgeAdj), int(iters), 1e-3, 0.95, 0.999, 1e-8, 1e-6, out.data_ptr(),
                                       None, st), "bg_surf_offset_opt")
     return out.reshape(nf, 32, 32, 3).cpu().numpy(), edge_wcs.cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------------------ sample.py:303-355
+def postprocess_cad(surf_vae, edge_vae, surfPos_cad, surfZ_cad, surfMask_cad, edge_pos_cad, edge_ncs_cad, edgeV_cad, edge_z_cad,
+                    edge_mask_cad, z_threshold: float = 0.2, iters: int = 200):
+    """One CAD through the reference's post-processing loop body (sample.py:303-355) up to, not including, construct_brep.
+
+    Inputs are the per-CAD slices of the cascade outputs exactly as sample.py:305-312 forms them from the batch arrays
+    (numpy; S face slots, E edge slots per face): surfPos (S,6) in model units, surfZ (S,48), surfMask (S,) True = padded,
+    edge_pos (S,E,6) in model units, edge_ncs (S,E,32,3) decoded edge curves, edgeV (S,E,6) predicted vertices (x3 frame),
+    edge_z (S,E,12), edge_mask (S,E) True = padded / duplicate.  surf_vae / edge_vae: the drop-in decoders (brepgen_b200.vae).
+    Returns (surf_wcs (F,32,32,3), edge_wcs (Eu,32,3), FaceEdgeAdj, EdgeVertexAdj, unique_vertices): the arguments of
+    construct_brep(surf_wcs, edge_wcs, FaceEdgeAdj, EdgeVertexAdj) (utils.py:819).  Raises AssertionError where the reference
+    prints '... failed' and skips the CAD."""
+    keep = ~np.asarray(surfMask_cad, dtype=bool)
+    emask = np.asarray(edge_mask_cad, dtype=bool)[keep]
+    epos, encs, ev = np.asarray(edge_pos_cad)[keep], np.asarray(edge_ncs_cad)[keep], np.asarray(edgeV_cad)[keep]
+    ez = np.asarray(edge_z_cad)[keep][~emask]
+    sz, spos = np.asarray(surfZ_cad)[keep], np.asarray(surfPos_cad)[keep]
+
+    ends = edge_endpoints(epos, encs, emask)                                           # sample.py:316-329
+    unique_vertices, vertex_dict = detect_shared_vertex(ev, emask, ends)               # 3-1
+    unique_faces, unique_edges, fea, eva = detect_shared_edge(unique_vertices, vertex_dict, ez, sz, z_threshold, emask)   # 3-2
+    with torch.no_grad():                                                              # sample.py:346-351
+        zf = torch.as_tensor(np.asarray(unique_faces, dtype=np.float32)).to(_dev())
+        surf_ncs = surf_vae(zf.unflatten(-1, (16, 3)).permute(0, 2, 1).unflatten(-1, (4, 4)).contiguous())
+        surf_ncs = surf_ncs.permute(0, 2, 3, 1).cpu().numpy()
+        ze = torch.as_tensor(np.asarray(unique_edges, dtype=np.float32)).to(_dev())
+        edge_ncs = edge_vae(ze.unflatten(-1, (4, 3)).permute(0, 2, 1).contiguous()).permute(0, 2, 1).cpu().numpy()
+    surf_wcs, edge_wcs = joint_optimize(surf_ncs, edge_ncs, spos, unique_vertices, eva, fea, len(edge_ncs), len(surf_ncs),
+                                        iters=iters)                                    # 3-3
+    return surf_wcs, edge_wcs, fea, eva, unique_vertices

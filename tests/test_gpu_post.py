@@ -95,3 +95,34 @@ def test_surface_fit_batched_over_many_faces():
                                             _ffi.current_stream()))
     got = out.reshape(reps, 6, 32, 32, 3).cpu().numpy()
     assert all(np.array_equal(got[r], one) for r in range(reps))
+
+
+def test_postprocess_cad_end_to_end():
+    """the whole loop body sample.py:303-355 (up to construct_brep) for one CAD: product pipeline (GPU cores + drop-in decoders)
+    against the oracle pipeline (numpy topology + oracle VAE decode + torch-CPU joint_optimize)"""
+    from brepgen_b200 import postprocess as P
+    from brepgen_b200.spec import edge_decoder_spec, surf_decoder_spec
+    from brepgen_b200.synth import synth_state_dict
+    from brepgen_b200.vae import build_synthetic_decoders
+    from oracle import vae as V
+    d = synth_cad(*CASES["box_c"])
+    sv, ev = build_synthetic_decoders(torch.device("cuda"), seed=2)
+    surf_wcs, edge_wcs, fea, eva, uv = P.postprocess_cad(sv, ev, d["surfPos"], d["surfZ"], d["surfMask"], d["edge_pos"], d["edge_ncs"],
+                                                         d["edgeV"], d["edge_z"], d["edge_mask"], Z_THRESHOLD)
+    c = select_cad(d)
+    ends = OP.edge_endpoints(c["edge_pos_cad"], c["edge_ncs_cad"], c["edge_mask_cad"])
+    ouv, ovd = OP.detect_shared_vertex(c["edgeV_cad"], c["edge_mask_cad"], ends)
+    ouf, oue, ofea, oeva = OP.detect_shared_edge(ouv, ovd, c["edge_z_cad"], c["surf_z_cad"], Z_THRESHOLD, c["edge_mask_cad"])
+    assert np.array_equal(eva, oeva) and [list(map(int, r)) for r in fea] == [list(map(int, r)) for r in ofea]
+    sd_s, sd_e = synth_state_dict(surf_decoder_spec(), 2), synth_state_dict(edge_decoder_spec(), 2)
+    with torch.no_grad():
+        zf = torch.as_tensor(ouf).unflatten(-1, (16, 3)).permute(0, 2, 1).unflatten(-1, (4, 4))
+        o_surf = V.surf_decode(sd_s, zf).permute(0, 2, 3, 1).numpy()
+        ze = torch.as_tensor(oue).unflatten(-1, (4, 3)).permute(0, 2, 1)
+        o_edge = V.edge_decode(sd_e, ze).permute(0, 2, 1).numpy()
+    o_swcs, o_ewcs = OP.joint_optimize(o_surf, o_edge, c["surf_pos_cad"], ouv, oeva, ofea, len(o_edge), len(o_surf))
+    e_err = np.abs(edge_wcs - o_ewcs).max() / np.abs(o_ewcs).max()
+    s_err = np.abs(surf_wcs - o_swcs).max() / np.abs(o_swcs).max()
+    print(f"postprocess_cad: edge_wcs rel max err {e_err:.2e}, surf_wcs {s_err:.2e}")
+    assert surf_wcs.shape == (6, 32, 32, 3) and edge_wcs.shape == (12, 32, 3)
+    assert e_err < 1e-3 and s_err < 2e-3
