@@ -30,6 +30,9 @@ for name, N, K, f16, relu, res in SHAPES:
     if relu:
         ref = ref.relu()
     err = float((out[rows].double() - ref.double()).norm() / ref.double().norm())
+    if os.environ.get("ONCE"):          # one launch per shape (for ncu --set full captures)
+        print(f"{env} {name:16s} M={M} N={N} K={K}: rel_l2={err:.2e}", flush=True)
+        continue
     for _ in range(2):
         call()
     torch.cuda.synchronize()
