@@ -14,13 +14,18 @@
 //   warps 4-11 (both) : epilogue; all 512 epilogue threads of the pair arrive on the leader's tmem-empty barrier (the
 //                       peer through a cluster-mapped address)
 //
-// Two epilogues (template parameter RES):
+// Three epilogues (template parameter RES):
 //   RES = 0  gemm_epilogue.cuh: fp16 outputs written directly, fp32 outputs transposed through shared memory; 6-stage ring.
 //   RES = 1  the in-place fp32 residual GEMMs  X += A W^T + b  (out-proj, FFN2), which are HBM-bound by construction
 //            (256 KB of residual in + result out per 128 x 256 tile against 2048 tensor cycles): each epilogue warp
 //            TMA-loads the residual 32 x 32 sub-tile into a swizzled staging buffer one chunk ahead, adds accumulator + bias
 //            there and TMA-stores it -- deep asynchronous queues instead of per-warp load / store bursts.  Measured at
 //            M = 256 000 (B = 64): out-proj 665 -> 580 us (4.07 TB/s), FFN2 571 -> 423 us (4.96 TB/s).  4-stage ring.
+//   RES = 2  fp16 outputs (q|k|v, FFN1): the direct form of RES = 0 writes 64 B per thread into 32 different rows per warp
+//            instruction (32 separate sectors); at K = 768 a tile's main loop is only 6144 cycles and that store pattern paced
+//            the whole kernel (timing experiment without the stores: q|k 602 -> 393 us, FFN1 388 -> 270 us).  Here every
+//            epilogue warp converts 32 rows x 64 columns, writes them as 128-byte rows into a swizzled staging buffer and
+//            TMA-stores the box (two buffers per warp, the store of chunk c overlaps the conversion of chunk c + 1).
 #include <stdlib.h>
 
 #include "bg_internal.h"
@@ -42,17 +47,21 @@ constexpr int BAR_BYTES = 256;
 constexpr int XPOSE_BYTES = 8 * 32 * GEMM_XPOSE_PITCH * 4;
 constexpr int SMEM_BYTES = NSTAGES * STAGE_BYTES + BAR_BYTES + XPOSE_BYTES + 1024;
 // RES == 1 (TMA-staged residual epilogue): 4-stage ring, 1 KB of barriers, then 8 warps x 3 buffers of 32 rows x 128 B
-constexpr int X_STAGES = 4;
+// RES == 2 (fp16 TMA-store epilogue): 5-stage ring, two staging buffers per warp
 constexpr int X_BUF_BYTES = 32 * 128;
-constexpr int X_BUFS = 3;
-constexpr int X_OFF_BAR = X_STAGES * STAGE_BYTES;
-constexpr int X_OFF_STG = X_OFF_BAR + 1024;
-constexpr int X_SMEM_BYTES = X_OFF_STG + 8 * X_BUFS * X_BUF_BYTES + 1024;
-static_assert(X_SMEM_BYTES <= 232448, "TMA-staged epilogue does not fit in shared memory");
+template <int RES> struct XL {                       // shared-memory layout of the staged-epilogue variants
+  static constexpr int STAGES = RES == 2 ? 5 : 4;
+  static constexpr int BUFS = RES == 2 ? 2 : 3;
+  static constexpr int OFF_BAR = STAGES * STAGE_BYTES;
+  static constexpr int OFF_STG = OFF_BAR + 1024;
+  static constexpr int SMEM_BYTES = OFF_STG + 8 * BUFS * X_BUF_BYTES + 1024;
+  static_assert(SMEM_BYTES <= 232448, "staged epilogue does not fit in shared memory");
+};
 
 // extra kernel parameter of the RES == 1 variant only
 template <int RES> struct EpiMaps {};
 template <> struct EpiMaps<1> { CUtensorMap x; };     // fp32 [M][ldo] residual / output matrix, box 32 x 32, SWIZZLE_128B
+template <> struct EpiMaps<2> { CUtensorMap x; };     // fp16 [M][ldo] output matrix, box 32 rows x 64 columns, SWIZZLE_128B
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -101,7 +110,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p_in,
                  const __grid_constant__ EpiMaps<RES> em) {
   const GemmParams p = gemm_resolve(p_in);
-  constexpr int STAGES = RES ? X_STAGES : NSTAGES;
+  constexpr int STAGES = RES ? XL<RES>::STAGES : NSTAGES;
+  constexpr int X_BUFS = XL<RES>::BUFS, X_OFF_BAR = XL<RES>::OFF_BAR, X_OFF_STG = XL<RES>::OFF_STG;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -118,7 +128,7 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    if constexpr (RES == 1) tma_prefetch_desc(&em.x);
+    if constexpr (RES != 0) tma_prefetch_desc(&em.x);
   }
   if (warp == 1 && elect_one()) {
     for (int i = 0; i < STAGES; ++i) {
@@ -261,6 +271,50 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           ++q;
         }
+      } else if constexpr (RES == 2) {
+        // ---- fp16 output through a swizzled staging buffer and TMA stores: out = fp16(relu(acc + bias)) ----
+        mbar_wait(&tfull[acc], accphase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BN + half * (BN / 2);
+#pragma unroll 1
+        for (int c = 0; c < BN / 2 / 64; ++c) {              // two chunks of 64 columns per warp
+          uint32_t r[64];
+          tmem_ld_32x32b_x32(taddr + c * 64, r);
+          tmem_ld_32x32b_x32(taddr + c * 64 + 32, r + 32);
+          const uint32_t b = q & 1;
+          if (lane == 0) bulk_wait_read<1>();                // the store that last read buffer b (two chunks ago) is done
+          __syncwarp();
+          tmem_ld_wait();
+          const int col0 = colbase + c * 64;
+          const uint32_t rowaddr = smem_u32(xstg + b * X_BUF_BYTES) + lane * 128;   // this thread's output row (64 x fp16)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[8 * j + i]);
+            if (p.bias) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + 2 * j);
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + 2 * j + 1);
+              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+            }
+            __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+            __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
+            st_shared_v4(rowaddr + ((j ^ (lane & 7)) << 4), *reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                         *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+          }
+          fence_proxy_async_smem();                          // generic-proxy writes -> visible to the TMA store
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&em.x, xstg + b * X_BUF_BYTES, col0, row0);    // rows >= M are clipped by the tensor map
+            bulk_commit();
+          }
+          ++q;
+        }
       } else {
         mbar_wait(&tfull[acc], accphase);
         tc_fence_after();
@@ -272,7 +326,7 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       acc ^= 1;
       if (acc == 0) accphase ^= 1;
     }
-    if constexpr (RES == 1) {
+    if constexpr (RES != 0) {
       if (lane == 0) bulk_wait_all();   // every TMA store of this thread has completed before the CTA may exit
     }
   }
@@ -290,10 +344,15 @@ int launch_gemm2_f16(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap&
   const int max_clusters = num_sms() / 2;
   const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
   if (!p.out_f16 && p.resid != nullptr && p.resid == p.out && p.ldr == p.ldo && p.rowvec == nullptr) {
-    BG_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&gemm2_f16_kernel<1>), X_SMEM_BYTES));
+    BG_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&gemm2_f16_kernel<1>), XL<1>::SMEM_BYTES));
     EpiMaps<1> em;
     BG_TRY(make_tmap_2d_f32(&em.x, p.out, (uint64_t)p.M, (uint64_t)p.N, (uint64_t)p.ldo, 32, 32));
-    gemm2_f16_kernel<1><<<2 * clusters, 384, X_SMEM_BYTES, st>>>(tmA, tmB, p, em);
+    gemm2_f16_kernel<1><<<2 * clusters, 384, XL<1>::SMEM_BYTES, st>>>(tmA, tmB, p, em);
+  } else if (p.out_f16 && p.ldo % 8 == 0) {
+    BG_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&gemm2_f16_kernel<2>), XL<2>::SMEM_BYTES));
+    EpiMaps<2> em;
+    BG_TRY(make_tmap_2d_f16(&em.x, p.out, (uint64_t)p.M, (uint64_t)p.N, (uint64_t)p.ldo, 32, 64));
+    gemm2_f16_kernel<2><<<2 * clusters, 384, XL<2>::SMEM_BYTES, st>>>(tmA, tmB, p, em);
   } else {
     BG_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&gemm2_f16_kernel<0>), SMEM_BYTES));
     gemm2_f16_kernel<0><<<2 * clusters, 384, SMEM_BYTES, st>>>(tmA, tmB, p, EpiMaps<0>{});
