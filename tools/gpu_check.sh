@@ -1,5 +1,5 @@
 #!/bin/bash
-set -x
-timeout 200 python tools/gemm_time.py
-timeout 900 python -m pytest tests/test_gpu_ops.py tests/test_gpu_denoisers.py -x -q 2>&1 | tail -3
-timeout 120 python tools/profile_forward.py --kind edgepos --batch 64 --iters 3 --time
+for x in "" _x1 _x2 _x3; do
+  echo "lib=$x"
+  BG_LIB=$PWD/brepgen_b200/libbrepgen_b200$x.so timeout 200 python tools/attn_check.py 2>&1 | tail -2
+done
