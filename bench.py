@@ -462,7 +462,7 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cores, desc, used = cpu_reference_sample(S0, S, E, 1, best_cpu_threads())
+        v, cores, desc, used = cpu_reference_sample(S0, S, E, 3, best_cpu_threads())      # ~10-20 s of CPU work
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": used, "sample": desc}
 
     if rank == 0:

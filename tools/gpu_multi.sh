@@ -1,7 +1,6 @@
 #!/bin/bash
-# 2-GPU check of the bench contract (torchrun, NCCL): weak scaling + the final all_gather inside the e2e region
+# N-GPU check of the bench contract (torchrun, NCCL): weak scaling + the final all_gather inside the e2e region
+N=${N:-2}; B=${B:-64}
 set -x
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --batch 64 --steps 2 --warmup 1 > gpurun_out/bench_2gpu_b64.json 2> gpurun_out/bench_2gpu_b64.err
-tail -c 1500 gpurun_out/bench_2gpu_b64.json; tail -5 gpurun_out/bench_2gpu_b64.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 1 --warmup 0 > gpurun_out/bench_2gpu_ref.json 2> gpurun_out/bench_2gpu_ref.err
-tail -c 600 gpurun_out/bench_2gpu_ref.json
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --batch $B --steps 2 --warmup 1 > gpurun_out/bench_${N}gpu_b$B.json 2> gpurun_out/bench_${N}gpu_b$B.err
+tail -c 1200 gpurun_out/bench_${N}gpu_b$B.json; tail -3 gpurun_out/bench_${N}gpu_b$B.err
