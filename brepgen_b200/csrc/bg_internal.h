@@ -49,9 +49,6 @@ int make_tmap_2d_f16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
 // 2-D fp32 row-major [rows][cols], row pitch ld (elements); box = {box_cols (<= 32: 128-byte swizzle span), box_rows}
 int make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                      uint32_t box_cols);
-// 3-D fp16 [batch][rows][cols] (row pitch ld, batch pitch = rows*ld); box = {64, box_rows, 1}; SWIZZLE_128B.
-int make_tmap_3d_f16(CUtensorMap* out, const void* base, uint64_t batch, uint64_t rows, uint64_t cols, uint64_t ld,
-                     uint32_t box_rows);
 
 // ---- tcgen05 GEMM:  out[M,N] = epilogue( A[M,K] (fp16, pitch lda) * W[N,K]^T (fp16, pitch ldw) ) ----
 struct GemmEpilogue {

@@ -100,12 +100,4 @@ int make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
   return encode(out, base, 2, dims, strides, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
 }
 
-int make_tmap_3d_f16(CUtensorMap* out, const void* base, uint64_t batch, uint64_t rows, uint64_t cols, uint64_t ld,
-                     uint32_t box_rows) {
-  cuuint64_t dims[3] = {cols, rows, batch};
-  cuuint64_t strides[2] = {ld * 2, rows * ld * 2};
-  cuuint32_t box[3] = {64, box_rows, 1};
-  return encode(out, base, 3, dims, strides, box);
-}
-
 }  // namespace bg
