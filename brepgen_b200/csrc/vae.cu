@@ -17,11 +17,25 @@
 #include "../../include/brepgen_b200.h"
 #include "bg_internal.h"
 
+#include <stdlib.h>
+
 namespace bg {
 namespace {
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 inline int round64(int k) { return (k + 63) / 64 * 64; }
+
+// Number of product terms of the compensated GEMMs, fixed per handle at creation:
+//   3: A_hi W_hi + A_lo W_hi + A_hi W_lo   (activations AND weights split; 9.4e-5 / 3.6e-5 against the oracle)
+//   2: A_hi W_hi + A_hi W_lo               (weights split only: the systematic part of the fp16 error) -- 1/3 less GEMM work
+//                                           and no lo plane in the im2col matrices
+// Measured on B200 against the fp32 oracle (bar 1e-3): edge decoder 4.1-4.4e-4 with 2 terms -> default 2 (-27 % time);
+// surface decoder 1.3e-3 and the encoders 6.6-9e-4 with 2 terms -> they keep 3.  BREPGEN_B200_VAE_TERMS = 2 | 3 overrides.
+int vae_terms_for(int kind) {
+  const char* e = getenv("BREPGEN_B200_VAE_TERMS");
+  if (e && (atoi(e) == 2 || atoi(e) == 3)) return atoi(e);
+  return kind == 1 ? 2 : 3;
+}
 
 // ------------------------------------------------------------------------------------------------ kernels
 // Compensated fp16 products.  Every GEMM of the decoders computes  A_hi W_hi + A_lo W_hi + A_hi W_lo  (hi = fp16(v),
@@ -30,7 +44,7 @@ inline int round64(int k) { return (k + 63) / 64 * 64; }
 // ~30 chained convolutions otherwise accumulate 1.9e-3 of fp16 rounding; decode is 0.13 % of the cascade's FLOPs.
 // weights [Cout][Cin][taps] fp32 -> [Cout_pad][3 * Kpad] fp16 with k = tap * Cin + cin (zero padded)
 __global__ void pack_conv_kernel(const float* __restrict__ w, __half* __restrict__ dst, int Cout, int Cin, int taps, int Kpad,
-                                 int Cout_pad) {
+                                 int Cout_pad, int terms) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)Cout_pad * Kpad) return;
   const int co = (int)(i / Kpad), k = (int)(i % Kpad);
@@ -39,21 +53,21 @@ __global__ void pack_conv_kernel(const float* __restrict__ w, __half* __restrict
     const int tap = k / Cin, ci = k % Cin;
     v = w[((size_t)co * Cin + ci) * taps + tap];
   }
-  const __half hi = __float2half_rn(v);
-  dst[(size_t)co * 3 * Kpad + k] = hi;
-  dst[(size_t)co * 3 * Kpad + Kpad + k] = hi;
-  dst[(size_t)co * 3 * Kpad + 2 * Kpad + k] = __float2half_rn(v - __half2float(hi));
+  const __half hi = __float2half_rn(v), lo = __float2half_rn(v - __half2float(hi));
+  dst[(size_t)co * 3 * Kpad + k] = hi;                                  // 3 terms: [W_hi | W_hi | W_lo]
+  dst[(size_t)co * 3 * Kpad + Kpad + k] = terms == 3 ? hi : lo;         // 2 terms: [W_hi | W_lo | (unused)]
+  dst[(size_t)co * 3 * Kpad + 2 * Kpad + k] = lo;
 }
 // plain linear [N][K] fp32 -> rows [row0, row0+N) of a [*][3K] hi|hi|lo operand
-__global__ void pack_linear_split_kernel(const float* __restrict__ w, __half* __restrict__ dst, int N, int K, int row0) {
+__global__ void pack_linear_split_kernel(const float* __restrict__ w, __half* __restrict__ dst, int N, int K, int row0, int terms) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)N * K) return;
   const int n = (int)(i / K), k = (int)(i % K);
   const float v = w[i];
-  const __half hi = __float2half_rn(v);
+  const __half hi = __float2half_rn(v), lo = __float2half_rn(v - __half2float(hi));
   dst[(size_t)(row0 + n) * 3 * K + k] = hi;
-  dst[(size_t)(row0 + n) * 3 * K + K + k] = hi;
-  dst[(size_t)(row0 + n) * 3 * K + 2 * K + k] = __float2half_rn(v - __half2float(hi));
+  dst[(size_t)(row0 + n) * 3 * K + K + k] = terms == 3 ? hi : lo;
+  dst[(size_t)(row0 + n) * 3 * K + 2 * K + k] = lo;
 }
 __device__ __forceinline__ void store_hl(__half* dst, int lo_off, float v) {
   const __half hi = __float2half_rn(v);
@@ -343,6 +357,7 @@ using namespace bg;
 
 struct BgVae {
   int kind = 0;                 // 0 surface decoder, 1 edge decoder, 2 surface encoder, 3 edge encoder
+  int terms = 3;                // product terms of the compensated GEMMs (vae_terms_for)
   char* arena = nullptr;
   size_t arena_bytes = 0;
   float *pq_w = nullptr, *pq_b = nullptr, *up_kernel = nullptr;
@@ -373,6 +388,7 @@ struct VPacker {
   bool dry = true;
   cudaStream_t st = nullptr;
   int err = 0;
+  int terms = 3;
 
   const float* find(const std::string& name, int64_t numel) {
     auto it = by_name.find(name);
@@ -418,7 +434,7 @@ struct VPacker {
     c.w = take<__half>((size_t)c.cout_pad * 3 * c.kpad);
     if (!dry && w && !err) {
       const size_t tot = (size_t)c.cout_pad * c.kpad;
-      pack_conv_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(w, c.w, cout, cin, taps, c.kpad, c.cout_pad);
+      pack_conv_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(w, c.w, cout, cin, taps, c.kpad, c.cout_pad, terms);
       err = check_launch("pack_conv_kernel launch");
     }
     if (bias) {
@@ -443,7 +459,7 @@ struct VPacker {
       const float* w = find(a + "." + names[i] + ".weight", (int64_t)C * C);
       const float* b = find(a + "." + names[i] + ".bias", C);
       if (!dry && w && b && !err) {
-        pack_linear_split_kernel<<<(C * C + 255) / 256, 256, 0, st>>>(w, c.w, C, C, i * C);
+        pack_linear_split_kernel<<<(C * C + 255) / 256, 256, 0, st>>>(w, c.w, C, C, i * C, terms);
         err = check_launch("pack_linear_split_kernel launch");
         if (!err) err = check_cuda(cudaMemcpyAsync(c.bias + i * C, b, C * 4, cudaMemcpyDeviceToDevice, st), "copy");
       }
@@ -624,6 +640,7 @@ struct Ctx {
   cudaStream_t st;
   size_t N;
   VaeWs w;
+  int terms = 3;
 };
 
 // A: [rows][2 * cv.kpad] fp16 = [A_hi | A_lo]
@@ -635,8 +652,12 @@ int gemm(const Ctx& c, const __half* A, const Conv& cv, size_t rows, float* out3
   ep.bias = cv.bias;
   ep.resid = resid;
   ep.ldr = cv.cout_pad;
-  ep.a_kwrap = 2 * cv.kpad;      // [A_hi | A_lo | A_hi] x [W_hi | W_hi | W_lo]
-  return launch_gemm_f16(c.st, A, 2 * cv.kpad, cv.w, 3 * cv.kpad, (int)rows, cv.cout_pad, 3 * cv.kpad, ep);
+  if (c.terms == 3) {
+    ep.a_kwrap = 2 * cv.kpad;    // [A_hi | A_lo | A_hi] x [W_hi | W_hi | W_lo]
+    return launch_gemm_f16(c.st, A, 2 * cv.kpad, cv.w, 3 * cv.kpad, (int)rows, cv.cout_pad, 3 * cv.kpad, ep);
+  }
+  ep.a_kwrap = cv.kpad;          // [A_hi | A_hi] x [W_hi | W_lo]  (the lo plane of A is not read)
+  return launch_gemm_f16(c.st, A, 2 * cv.kpad, cv.w, 3 * cv.kpad, (int)rows, cv.cout_pad, 2 * cv.kpad, ep);
 }
 int groupnorm(const Ctx& c, const float* x, int P, int C, int G, float eps, const Norm& n, int act, const float* resid,
               float* out32, __half* out16) {
@@ -652,7 +673,7 @@ int im2col2d(const Ctx& c, const __half* in, int H, int W, int C, int up, int kp
   const int vec = (C % 8 == 0) ? 8 : 1;
   const int pad_lo = stride == 1 ? 1 : 0;
   const size_t tot = c.N * (size_t)(H * up / stride) * (W * up / stride) * (kpad / vec);
-  for (int part = 0; part < 2; ++part) {   // hi plane, then lo plane of the [hi | lo] activation
+  for (int part = 0; part < c.terms - 1; ++part) {   // hi plane, then (3-term mode) lo plane of the [hi | lo] activation
     im2col2d_kernel<<<grid_for(tot), 256, 0, c.st>>>(in + part * C, 2 * C, c.w.A + part * kpad, 2 * kpad, H, W, C, up, stride, pad_lo, kpad, tot, vec);
     BG_TRY(check_launch("im2col2d_kernel launch"));
   }
@@ -661,7 +682,7 @@ int im2col2d(const Ctx& c, const __half* in, int H, int W, int C, int up, int kp
 int im2col1d(const Ctx& c, const __half* in, int L, int C, int ks, int kpad) {
   const int vec = (C % 8 == 0) ? 8 : 1;
   const size_t tot = c.N * (size_t)L * (kpad / vec);
-  for (int part = 0; part < 2; ++part) {
+  for (int part = 0; part < c.terms - 1; ++part) {
     im2col1d_kernel<<<grid_for(tot), 256, 0, c.st>>>(in + part * C, 2 * C, c.w.A + part * kpad, 2 * kpad, L, C, ks, kpad, tot, vec);
     BG_TRY(check_launch("im2col1d_kernel launch"));
   }
@@ -728,7 +749,9 @@ int bg_vae_create(int kind, const BgNamedTensor* weights, int n_weights, void* s
   BG_TRY(bg_check_device());
   BgVae* m = new BgVae();
   m->kind = kind;
+  m->terms = vae_terms_for(kind);
   VPacker pk;
+  pk.terms = m->terms;
   for (int i = 0; i < n_weights; ++i) pk.by_name[weights[i].name] = &weights[i];
   pk.st = reinterpret_cast<cudaStream_t>(stream);
   int s = pack_vae(m, pk);
@@ -770,6 +793,7 @@ int bg_vae_decode_hw(BgVae* m, const float* z, int N, int hw, float* out, void* 
   Ctx c;
   c.st = reinterpret_cast<cudaStream_t>(stream);
   c.N = (size_t)N;
+  c.terms = m->terms;
   char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
   c.w = carve_vae(base, m->kind, c.N);
   if (c.w.bytes + (size_t)(base - reinterpret_cast<char*>(workspace)) > workspace_bytes)
@@ -847,6 +871,7 @@ int bg_vae_encode(BgVae* m, const float* xin, int N, int hw, float* out, void* w
   Ctx c;
   c.st = reinterpret_cast<cudaStream_t>(stream);
   c.N = (size_t)N;
+  c.terms = m->terms;
   char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
   c.w = carve_vae(base, m->kind, c.N);
   if (c.w.bytes + (size_t)(base - reinterpret_cast<char*>(workspace)) > workspace_bytes)
