@@ -204,3 +204,33 @@ def test_step_noise_key_depends_on_seed_rank_and_stage():
     assert a._philox_seed != b._philox_seed and a._philox_offset == b._philox_offset == 0
     b.set_noise_seed(5, 0, 3)
     assert a._philox_seed == b._philox_seed
+
+
+def test_valid_token_flops_reduce_to_dense_when_nothing_is_masked():
+    """bench.py's valid-token FLOP count (the dense formulas with L -> L_valid) equals the dense-algorithmic
+    count for all-valid masks and shrinks quadratically in the attention term"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    S0, S, E, B = 50, 100, 40, 3
+    dense = bench.cascade_flops_per_brep(S0, S, E)
+    sm = torch.zeros(B, S, dtype=torch.bool)
+    em = torch.zeros(B, S, E, dtype=torch.bool)
+    assert abs(bench.cascade_flops_valid_tokens(S0, S, E, sm, em) / dense - 1) < 1e-12
+    sm[:, S // 2:] = True
+    em[:, S // 2:] = True
+    half = bench.cascade_flops_valid_tokens(S0, S, E, sm, em)
+    assert 0.25 < half / dense < 0.5           # linear terms halve, the L^2 attention term quarters
+    assert abs(dense / 1e12 - 1980.1) < 0.1    # SURVEY.md 8d table: 1980.1 TF per B-rep
+
+
+def test_reference_loader_runs_the_reference_classes_when_available():
+    from oracle.reference_loader import load_reference_network, reference_dir
+    if reference_dir() is None:
+        pytest.skip("neither /root/reference nor baseline/_ref present")
+    net = load_reference_network()
+    m = net.SurfPosNet(False).eval()
+    with torch.no_grad():
+        y = m(torch.zeros(1, 4, 6), torch.tensor([3]), None)
+    assert y.shape == (1, 4, 6)

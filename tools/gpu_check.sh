@@ -1,16 +1,8 @@
 #!/bin/bash
+# one gpurun call: the whole GPU test suite, smoke(), the default bench (BASELINE configs[2], B = 256) and the reference arm
+#   gpurun --timeout 3000 -- 'bash tools/gpu_check.sh > gpurun_out/gpu_check.log 2>&1'
 set -x
-BREPGEN_B200_VAE_TERMS=2 timeout 600 python -m pytest tests/test_gpu_vae.py -q -s 2>&1 | grep -E "rel_l2|passed|failed|Error" | head -20
-timeout 600 python -m pytest tests/test_gpu_vae.py -q -s 2>&1 | grep -E "rel_l2|passed|failed" | head -20
-cat > /tmp/vt.py <<'PY'
-import torch, time, sys
-sys.path.insert(0, '.')
-from brepgen_b200.vae import build_synthetic_decoders
-sv, ev = build_synthetic_decoders(torch.device('cuda'))
-zs = torch.randn(64 * 100, 3, 4, 4, device='cuda'); ze = torch.randn(64 * 4000, 3, 4, device='cuda')
-for _ in range(2): sv(zs); ev(ze)
-torch.cuda.synchronize(); t0 = time.time(); sv(zs); torch.cuda.synchronize(); t1 = time.time(); ev(ze); torch.cuda.synchronize(); t2 = time.time()
-print(f"decode B=64: surface {1e3*(t1-t0):.1f} ms, edge {1e3*(t2-t1):.1f} ms")
-PY
-BREPGEN_B200_VAE_TERMS=2 python /tmp/vt.py
-BREPGEN_B200_VAE_TERMS=3 python /tmp/vt.py
+timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -6
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 900 python bench.py --impl reference --steps 3 --warmup 3 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; tail -c 900 gpurun_out/bench_reference.json
+timeout 1800 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; tail -c 3200 gpurun_out/bench_default.json
