@@ -90,3 +90,14 @@ def ptr(t) -> Optional[int]:
 def current_stream() -> int:
     import torch
     return torch.cuda.current_stream().cuda_stream
+
+
+# Kernels launched through CUDA-graph replays do not pass through the library's host-side launch counter (bg_launch_count
+# counts a captured launch once, at capture time).  Code that replays a captured sequence adds `launches per replay` here,
+# so that bench.py's `gpu_launches` = bg_launch_count() + replayed_launches is the number of kernels that really ran.
+replayed_launches = 0
+
+
+def note_replay(launches_per_replay: int, times: int = 1) -> None:
+    global replayed_launches
+    replayed_launches += int(launches_per_replay) * int(times)

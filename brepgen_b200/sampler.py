@@ -136,10 +136,13 @@ class Cascade:
         xb.copy_(x0)
         step.fill_(-1)
         g = torch.cuda.CUDAGraph()
+        l0 = lib.bg_launch_count()
         with torch.cuda.graph(g):
             body()
+        per_replay = lib.bg_launch_count() - l0
         for _ in range(T):
             g.replay()
+        _ffi.note_replay(per_replay, T)
         self.ddpm.advance_philox(n, T)
         self.last_graph_steps = getattr(self, "last_graph_steps", 0) + T
         return xb

@@ -120,14 +120,16 @@ class _VaeModule(nn.Module):
                     zs, os_ = torch.empty_like(z[:step]), torch.empty_like(out[:step])
                     run(z[:step].data_ptr(), step, os_.data_ptr())           # warm-up outside the capture
                     graph = torch.cuda.CUDAGraph()
+                    l0 = _ffi.lib().bg_launch_count()
                     with torch.cuda.graph(graph):
                         run(zs.data_ptr(), step, os_.data_ptr())
-                    g = self._graphs[key] = (graph, zs, os_)
-                graph, zs, os_ = g
+                    g = self._graphs[key] = (graph, zs, os_, _ffi.lib().bg_launch_count() - l0)
+                graph, zs, os_, per_replay = g
                 for c in range(full):
                     zs.copy_(z[c * step:(c + 1) * step])
                     graph.replay()
                     out[c * step:(c + 1) * step].copy_(os_)
+                _ffi.note_replay(per_replay, full)
                 lo0 = full * step
             else:
                 lo0 = 0
