@@ -86,9 +86,6 @@ struct AttnArgs {
   const int* seq_len = nullptr;
 };
 int launch_attention(cudaStream_t st, const AttnArgs& a);
-int launch_attention_rowsplit(cudaStream_t st, const AttnArgs& a, int poly);   // attn_rs.cu, L > 128 only
-bool attention_persistent_supported(const AttnArgs& a);                       // attn_ps.cu
-int launch_attention_persistent(cudaStream_t st, const AttnArgs& a, int poly);
 // builds blk_list/blk_count from key_mask ([B,L]); nkb = ceil(L/128)
 int launch_build_block_list(cudaStream_t st, const uint8_t* key_mask, int B, int L, int* blk_list, int* blk_count,
                             uint32_t* blk_words = nullptr);

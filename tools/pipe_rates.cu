@@ -13,7 +13,8 @@
 constexpr int ITER = 2000;
 constexpr int UNROLL = 16;
 
-enum Op { FFMA, FFMA2_RRR, FFMA2, FADD2, FMUL2, FMNMX3, F2FP, MUFU, MUFU_FFMA2_1_4, MUFU_FFMA_1_8, FFMA2_F2FP, FFMA2_FMNMX3 };
+enum Op { FFMA, FFMA2_RRR, FFMA2, FADD2, FMUL2, FMNMX3, F2FP, MUFU, MUFU_FFMA2_1_4, MUFU_FFMA_1_8, FFMA2_F2FP, FFMA2_FMNMX3,
+          MUFU_H2, ADD_F32_F16, MUFU_3OTHER, MUFU_7OTHER, MUFU_H2_7OTHER, HADD2, FMNMX };
 
 template <int OP>
 __global__ void rate_kernel(float* out, long long* cycles, float seed) {
@@ -64,6 +65,32 @@ __global__ void rate_kernel(float* out, long long* cycles, float seed) {
         x[i] = __uint_as_float(h & 0x3fffffffu);
       } else if (OP == MUFU) {
         asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x[i]));
+      } else if (OP == MUFU_H2) {             // two fp16 exponentials per lane and instruction
+        unsigned h = __float_as_uint(x[i]);
+        asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(h));
+        x[i] = __uint_as_float(h);
+      } else if (OP == ADD_F32_F16) {         // mixed-precision add (PTX 8.6, sm_100): f32 accumulator += f16
+        unsigned short hh = (unsigned short)(__float_as_uint(y[i]) & 0x3fffu);
+        asm volatile("add.rn.f32.f16 %0, %1, %0;" : "+f"(x[i]) : "h"(hh));
+      } else if (OP == HADD2) {
+        unsigned h = __float_as_uint(x[i]) & 0x3fff3fffu, g = __float_as_uint(y[i]) & 0x3fff3fffu;
+        asm volatile("add.rn.f16x2 %0, %0, %1;" : "+r"(h) : "r"(g));
+        x[i] = __uint_as_float(h);
+      } else if (OP == FMNMX) {
+        asm volatile("max.f32 %0, %0, %1;" : "+f"(x[i]) : "f"(y[i]));
+      } else if (OP == MUFU_3OTHER || OP == MUFU_7OTHER || OP == MUFU_H2_7OTHER) {
+        // one exponential followed by 3 / 7 independent single-cycle-class instructions (FFMA): can ONE warp keep the XU pipe
+        // busy while it also issues its other work?
+        if (OP == MUFU_H2_7OTHER) {
+          unsigned h = __float_as_uint(x[i]);
+          asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(h));
+          x[i] = __uint_as_float(h);
+        } else {
+          asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x[i]));
+        }
+        constexpr int NO = OP == MUFU_3OTHER ? 3 : 7;
+#pragma unroll
+        for (int k = 0; k < NO; ++k) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(y[(i + k) % UNROLL]) : "f"(a), "f"(b));
       } else if (OP == MUFU_FFMA2_1_4) {      // the attention pattern: 1 MUFU per 4 packed FMA-pipe instructions
         if ((i & 3) == 0) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x[i]));
         asm volatile(
@@ -135,7 +162,14 @@ int main() {
   run<FMNMX3>("FMNMX3 (max.f32 a,b,c)", 1);
   run<F2FP>("F2FP.F16.F32.PACK_AB", 1);
   run<MUFU>("MUFU.EX2", 1);
+  run<FMNMX>("FMNMX (max.f32 a,b)", 1);
+  run<MUFU_H2>("MUFU.EX2.F16x2", 1);
+  run<ADD_F32_F16>("add.rn.f32.f16 (mixed)", 1);
+  run<HADD2>("HADD2", 1);
   printf("mixed (cycles per unroll step = the group in the name):\n");
+  run<MUFU_3OTHER>("1 MUFU + 3 FFMA per step", 1);
+  run<MUFU_7OTHER>("1 MUFU + 7 FFMA per step", 1);
+  run<MUFU_H2_7OTHER>("1 MUFU.F16x2 + 7 FFMA per step", 1);
   run<MUFU_FFMA2_1_4>("1/4 MUFU + 1 FFMA2 per step", 1);
   run<MUFU_FFMA_1_8>("1/8 MUFU + 1 FFMA per step", 1);
   run<FFMA2_F2FP>("FFMA2 + F2FP per step", 1);
