@@ -75,6 +75,18 @@ struct AttnParams {
   int probe;          // early non-blocking mbarrier probes
 };
 
+// -DBG_ATTN_TRACE (`make trace`, tools/attn_trace.py): clock64 stamps of the softmax thread of row 0 of both tiles of one CTA
+#ifdef BG_ATTN_TRACE
+__device__ long long g_attn_trace[2][64][8];
+#define BG_TR(pt)                                                                                                    \
+  do {                                                                                                               \
+    if ((threadIdx.x & 127) == 0 && blockIdx.x == 3 && blockIdx.y == 5 && blockIdx.z == 1 && it < 64)                \
+      g_attn_trace[t][it][pt] = clock64();                                                                           \
+  } while (0)
+#else
+#define BG_TR(pt)
+#endif
+
 // PM: 4-bit mask over the 4 element pairs of each 8-key chunk whose exp2 runs as a polynomial on the FMA pipe instead of
 // MUFU.EX2 (the XU pipe, 16 ex2/clk/SM, is the binding unit of d=64 attention on B200)
 // PT: P goes to TENSOR MEMORY (tcgen05.st, two fp16 per column) and the PV MMA takes its A operand from TMEM -- per key
@@ -293,8 +305,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
       const uint4 iw = *reinterpret_cast<const uint4*>(maskw + it * 4);
       const uint32_t inval[4] = {iw.x, iw.y, iw.z, iw.w};
 
+      BG_TR(0);
       if (HW) named_bar_sync(3 + t, 160);
       else if (!s_ready) mbar_wait(&s_full[t], it & 1);
+      BG_TR(6);
       tc_fence_after();
       float s[128];
 #pragma unroll
@@ -303,6 +317,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
       bool pv_ready = it == 0;
       if (!HW && it > 0 && p.probe) pv_ready = mbar_test_wait(&pv_full[t * C::PB + (it - 1) % C::PB], ((it - 1) / C::PB) & 1);
       tmem_ld_wait();
+      BG_TR(1);
       tc_fence_before();
       mbar_arrive(&s_free[t]);          // S_t may be overwritten by QK^T of the next block
 
@@ -344,10 +359,13 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
           if (need) m_ref = m_new;
         }
       }
+      BG_TR(2);
       if (it >= C::PB && !pv_ready) wait_pv(it - C::PB);   // the PV MMA that read this P buffer has finished
       // probe the next block's scores now; the answer is consumed at the top of the next iteration
       s_ready = (!HW && p.probe && it + 1 < nblk) ? mbar_test_wait(&s_full[t], (it + 1) & 1) : false;
+      BG_TR(7);
       if (pingpong) named_bar_sync(1 + t, 256);
+      BG_TR(3);
       const uint32_t sP = sP0 + (it % C::PB) * P_BYTES;
       const float2 c2 = make_float2(c, c);
       const float2 nmc2 = make_float2(-m_ref * c, -m_ref * c);
@@ -405,8 +423,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
       } else {
         fence_proxy_async_smem();       // generic-proxy writes of P -> visible to the tensor core (async proxy)
       }
+      BG_TR(4);
       mbar_arrive(&p_full[t]);
       l += (acc.x + acc.y) + (acc1.x + acc1.y);
+      BG_TR(5);
     }
 
     float o[DH];
@@ -531,6 +551,12 @@ int launch_attention(cudaStream_t st, const AttnArgs& a) {
   if (poly == 2) return launch_nt<2, 0xA, 0, 1>(st, tm, p);
   return launch_nt<2, 0x8, 0, 1>(st, tm, p);
 }
+
+#ifdef BG_ATTN_TRACE
+extern "C" int bg_debug_attn_trace(long long* host_out) {
+  return check_cuda(cudaMemcpyFromSymbol(host_out, g_attn_trace, sizeof(long long) * 2 * 64 * 8), "trace copy");
+}
+#endif
 
 int launch_build_block_list(cudaStream_t st, const uint8_t* key_mask, int B, int L, int* blk_list, int* blk_count,
                             uint32_t* blk_words) {
