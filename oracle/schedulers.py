@@ -1,16 +1,18 @@
 """ORACLE (test infrastructure): CPU restatement of diffusers 0.27 DDPMScheduler / PNDMScheduler arithmetic.
 
-PARITY UNPINNED: diffusers==0.27 (requirements.txt:5 of the reference) is a third-party dependency
-that is absent from /root/reference and from this image, and the reference holds no golden vector for
-it.  This file restates the published algorithm and is anchored on the
-reference's call sites:
+diffusers==0.27 (requirements.txt:5 of the reference) is a third-party dependency that is absent from /root/reference and
+from this image, so its code cannot be executed here and the reference itself holds no golden vector for it.
+PINNED by the known answers of diffusers' own scheduler tests (tests/test_oracle_sched_kat.py): the full 1000-step DDPM
+loop with injected noise (|x| sum 258.9606) and the PRK + PLMS loops of PNDM (198.1318; beta_start = 0.01: 186.9482) over the
+deterministic dummy model of tests/schedulers/test_scheduler_{ddpm,pndm}.py are reproduced to diffusers' own tolerances.
+Further anchors: the reference's call sites
   ctor kwargs           sample.py:101-117 (PNDM: linear betas 1e-4..0.02, epsilon; DDPM: + clip_sample, range 3)
   set_timesteps(200)    sample.py:128,191,210,269   -> 209 PNDM entries, [:158] ends 255 -> 250
   set_timesteps(1000)   sample.py:144,224           -> [-250:] starts at t=249
   step(pred,t,x).prev_sample   sample.py:137,153,202,222,236,282
   add_noise             trainer.py:348 etc.
-and on structural invariants (tests/test_oracle_schedulers.py): x0-recovery, posterior-mean identity,
-DDIM identity for PNDM's transfer formula, PRK/PLMS table shape.
+and structural invariants (tests/test_host_logic.py): x0-recovery, posterior-mean identity, DDIM identity for PNDM's
+transfer formula, PRK/PLMS table shape.
 """
 from __future__ import annotations
 
