@@ -1,6 +1,11 @@
 """ORACLE (test infrastructure): CPU fp32 restatement of the two VAE decoders.
 
-PARITY UNPINNED.  The arithmetic lives in diffusers==0.27 (requirements.txt:5 of the reference), which is absent from
+2-D (surface) decoder leaves PINNED by diffusers' own known answers (tests/test_oracle_vae_kat.py): `_resnet2d` (with and
+without conv_shortcut), `_attn2d` and `_upsample2d` reproduce the expected output slices of diffusers'
+tests/models/test_layers_utils.py (ResnetBlock2DTests.test_resnet_default / test_restnet_with_use_in_shortcut,
+AttentionBlockTests.test_attention_block_default, Upsample2DBlockTests.test_upsample_default / test_upsample_with_conv) to 4
+decimals.  1-D leaves (ResConvBlock, SelfAttention1d, Upsample1d; diffusers has no known-answer test for them) and the 2-D
+encoder's Downsample2D remain PARITY UNPINNED.  The arithmetic lives in diffusers==0.27 (requirements.txt:5 of the reference), which is absent from
 /root/reference and from this image: `Decoder`, `UNetMidBlock2D`, `UpDecoderBlock2D`, `ResnetBlock2D`, `Attention`,
 `Upsample2D` (surface) and `ResConvBlock`, `SelfAttention1d`, `Upsample1d` (edge).  This file restates their published
 structure around the reference's own wrappers
@@ -32,23 +37,39 @@ def _gn(x, sd, name, groups, eps):
 
 
 # ------------------------------------------------------------------------------------------------ surface (2-D)
-def _resnet2d(sd: SD, name: str, x):
+def _resnet2d(sd: SD, name: str, x, temb_add=None):
+    """diffusers ResnetBlock2D (groups 32, eps 1e-6, swish).  `temb_add` (the projected time embedding, (N,C,1,1)) is None in
+    the VAE (temb_channels=None); it exists so that the block can be checked against diffusers' own known answers, which use
+    one (tests/test_oracle_vae_kat.py)."""
     h = F.conv2d(F.silu(_gn(x, sd, name + ".norm1", 32, 1e-6)), sd[name + ".conv1.weight"], sd[name + ".conv1.bias"], padding=1)
+    if temb_add is not None:
+        h = h + temb_add
     h = F.conv2d(F.silu(_gn(h, sd, name + ".norm2", 32, 1e-6)), sd[name + ".conv2.weight"], sd[name + ".conv2.bias"], padding=1)
     if name + ".conv_shortcut.weight" in sd:
         x = F.conv2d(x, sd[name + ".conv_shortcut.weight"], sd[name + ".conv_shortcut.bias"])
     return x + h
 
 
-def _attn2d(sd: SD, name: str, x):
+def _attn2d(sd: SD, name: str, x, n_head: int = 1):
+    """diffusers mid-block attention (GroupNorm 32 / 1e-6, softmax(q k^T / sqrt(dim_head)), residual).  The VAE uses ONE head of
+    dim_head = C (attention_head_dim = C); n_head exists for diffusers' known-answer test, which uses heads of dimension 1."""
     N, C, H, W = x.shape
     h = _gn(x, sd, name + ".group_norm", 32, 1e-6).view(N, C, H * W).transpose(1, 2)          # (N, HW, C)
-    q = h @ sd[name + ".to_q.weight"].t() + sd[name + ".to_q.bias"]
-    k = h @ sd[name + ".to_k.weight"].t() + sd[name + ".to_k.bias"]
-    v = h @ sd[name + ".to_v.weight"].t() + sd[name + ".to_v.bias"]
-    a = torch.softmax(q @ k.transpose(1, 2) / math.sqrt(C), dim=-1) @ v                       # 1 head, dim_head = C
+    dh = C // n_head
+    heads = lambda t: t.view(N, H * W, n_head, dh).transpose(1, 2)                            # (N, heads, HW, dh)
+    q = heads(h @ sd[name + ".to_q.weight"].t() + sd[name + ".to_q.bias"])
+    k = heads(h @ sd[name + ".to_k.weight"].t() + sd[name + ".to_k.bias"])
+    v = heads(h @ sd[name + ".to_v.weight"].t() + sd[name + ".to_v.bias"])
+    a = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(dh), dim=-1) @ v
+    a = a.transpose(1, 2).reshape(N, H * W, C)
     a = a @ sd[name + ".to_out.0.weight"].t() + sd[name + ".to_out.0.bias"]
     return x + a.transpose(1, 2).reshape(N, C, H, W)
+
+
+def _upsample2d(sd: SD, name: str, x):
+    """diffusers Upsample2D(use_conv=True): nearest 2x, then conv 3x3 pad 1"""
+    x = F.interpolate(x, scale_factor=2.0, mode="nearest")
+    return F.conv2d(x, sd[name + ".conv.weight"], sd[name + ".conv.bias"], padding=1)
 
 
 def surf_decode(sd: SD, z: torch.Tensor) -> torch.Tensor:
@@ -63,9 +84,7 @@ def surf_decode(sd: SD, z: torch.Tensor) -> torch.Tensor:
         for j in range(3):
             x = _resnet2d(sd, f"{d}.up_blocks.{i}.resnets.{j}", x)
         if i < 3:
-            x = F.interpolate(x, scale_factor=2.0, mode="nearest")
-            x = F.conv2d(x, sd[f"{d}.up_blocks.{i}.upsamplers.0.conv.weight"], sd[f"{d}.up_blocks.{i}.upsamplers.0.conv.bias"],
-                         padding=1)
+            x = _upsample2d(sd, f"{d}.up_blocks.{i}.upsamplers.0", x)
     x = F.silu(_gn(x, sd, f"{d}.conv_norm_out", 32, 1e-6))
     return F.conv2d(x, sd[f"{d}.conv_out.weight"], sd[f"{d}.conv_out.bias"], padding=1)
 

@@ -1,0 +1,64 @@
+"""CPU tests: the 2-D VAE leaves of oracle/vae.py against the known answers of diffusers' OWN layer tests.
+
+diffusers (requirements.txt:5 of the reference pins 0.27) is absent from the image; its tests/models/test_layers_utils.py
+publishes expected output slices for layers built under torch.manual_seed(0) with torch's default initialisers.  The torch
+modules below are created in the order diffusers' constructors create theirs, so they draw the same parameters from the
+same generator; the arithmetic under test is the oracle's.  Expected slices (output[0, -1, -3:, -3:]) and the 1e-3 tolerance
+are diffusers'."""
+import torch
+import torch.nn as nn
+
+from oracle import vae as V
+
+
+def _gn(prefix, C):
+    return {prefix + ".weight": torch.ones(C), prefix + ".bias": torch.zeros(C)}
+
+
+def _conv(prefix, m):
+    return {prefix + ".weight": m.weight.data, prefix + ".bias": m.bias.data}
+
+
+def _check(out, expected):
+    got = out[0, -1, -3:, -3:].flatten()
+    assert torch.allclose(got, torch.tensor(expected), atol=1e-3), got
+
+
+def _resnet_case(shortcut):
+    torch.manual_seed(0)
+    sample, temb = torch.randn(1, 32, 64, 64), torch.randn(1, 128)
+    # ResnetBlock2D.__init__(in_channels=32, temb_channels=128): norm1, conv1, time_emb_proj, norm2, conv2[, conv_shortcut]
+    conv1, tproj, conv2 = nn.Conv2d(32, 32, 3, padding=1), nn.Linear(128, 32), nn.Conv2d(32, 32, 3, padding=1)
+    sd = {**_gn("r.norm1", 32), **_gn("r.norm2", 32), **_conv("r.conv1", conv1), **_conv("r.conv2", conv2)}
+    if shortcut:
+        sd.update(_conv("r.conv_shortcut", nn.Conv2d(32, 32, 1)))
+    with torch.no_grad():
+        return V._resnet2d(sd, "r", sample, temb_add=tproj(torch.nn.functional.silu(temb))[:, :, None, None])
+
+
+def test_resnet_block_default():          # ResnetBlock2DTests.test_resnet_default
+    _check(_resnet_case(False), [-1.9010, -0.2974, -0.8245, -1.3533, 0.8742, -0.9645, -2.0584, 1.3387, -0.4746])
+
+
+def test_resnet_block_conv_shortcut():    # ResnetBlock2DTests.test_restnet_with_use_in_shortcut
+    _check(_resnet_case(True), [0.2226, -1.0791, -0.1629, 0.3659, -0.2889, -1.2376, 0.0582, 0.9206, 0.0044])
+
+
+def test_attention_block_default():       # AttentionBlockTests.test_attention_block_default (32 heads of dimension 1)
+    torch.manual_seed(0)
+    sample = torch.randn(1, 32, 64, 64)
+    q, k, v, o = (nn.Linear(32, 32) for _ in range(4))     # group_norm, query, key, value, proj_attn
+    sd = {**_gn("a.group_norm", 32), **_conv("a.to_q", q), **_conv("a.to_k", k), **_conv("a.to_v", v), **_conv("a.to_out.0", o)}
+    with torch.no_grad():
+        out = V._attn2d(sd, "a", sample, n_head=32)
+    _check(out, [-1.4975, -0.0038, -0.7847, -1.4567, 1.1220, -0.8962, -1.7394, 1.1319, -0.5427])
+
+
+def test_upsample_with_conv():            # Upsample2DBlockTests.test_upsample_with_conv
+    torch.manual_seed(0)
+    sample = torch.randn(1, 32, 32, 32)
+    sd = _conv("u.conv", nn.Conv2d(32, 32, 3, padding=1))
+    with torch.no_grad():
+        out = V._upsample2d(sd, "u", sample)
+    assert out.shape == (1, 32, 64, 64)
+    _check(out, [0.7145, 1.3773, 0.3492, 0.8448, 1.0839, -0.3341, 0.5956, 0.1250, -0.4841])
