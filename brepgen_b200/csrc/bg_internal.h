@@ -50,6 +50,24 @@ int make_tmap_2d_f16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
 int make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                      uint32_t box_cols);
 
+// 4-D fp16 channels-last activation [n][h][w][c] (c contiguous, pitch ldc elements per pixel); box = {64 channels, box_w,
+// box_h, box_n}; SWIZZLE_128B; out-of-range coordinates (the zero padding of a convolution) are filled with zeros
+int make_tmap_4d_f16(CUtensorMap* out, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t N, uint64_t ldc,
+                     uint32_t box_w, uint32_t box_h, uint32_t box_n);
+
+// Implicit-GEMM convolution (stride 1, "same" zero padding) over a channels-last activation [n][H][W][planes * C] fp16:
+// row m of the GEMM is output pixel m (n, y, x order), its K axis runs over (term, tap, channel): the A tile of k-block
+// (term, tap, 64-channel chunk) is the TMA box {64 channels, W, box_h, box_n} of the input shifted by the tap's offset, so
+// the im2col matrix exists only as shared-memory tiles (VAE decoders: network.py:1013-1040, 846-858).
+struct ConvGeom {
+  int taps = 0;            // 0: plain GEMM.  kh * kw
+  int kw = 1;              // taps per kernel row (1-D convolutions: kw = taps, H = 1)
+  int C = 0;               // channels per plane (multiple of 64)
+  int W = 0, H = 1, N = 0; // image extents and number of images;  W * H divides 128 or is a multiple of 128
+  int lo_plane = 0;        // 1: A is [hi | lo] (pitch 2C) and the middle term of a 3-term product reads the lo plane
+  int terms = 1;           // K = terms * taps * C: [A_hi W_hi (+ A_lo W_hi) + A_hi W_lo]
+};
+
 // ---- tcgen05 GEMM:  out[M,N] = epilogue( A[M,K] (fp16, pitch lda) * W[N,K]^T (fp16, pitch ldw) ) ----
 struct GemmEpilogue {
   void* out = nullptr;           // fp16 or fp32, pitch ldo (elements)
@@ -66,6 +84,7 @@ struct GemmEpilogue {
   int n_short = 0, k_short = 0;  // column tiles below n_short (a multiple of 256) use only the first k_short columns of K
   const int* m_dev = nullptr;    // optional device int: only min(M, *m_dev) rows are computed (token compaction)
   const int* row_map = nullptr;  // optional: rowvec is indexed with row_map[row] / rows_per_vec instead of row / rows_per_vec
+  ConvGeom conv;                 // conv.taps > 0: A is a channels-last image and the GEMM is an implicit convolution
 };
 int launch_gemm_f16(cudaStream_t st, const __half* A, int lda, const __half* W, int ldw, int M, int N, int K,
                     const GemmEpilogue& ep);

@@ -76,7 +76,7 @@ static int encode(CUtensorMap* out, const void* base, uint32_t rank, const cuuin
                   const cuuint32_t* box, CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_FLOAT16) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return set_error(BG_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
-  cuuint32_t estr[3] = {1, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(out, dtype, rank, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -90,6 +90,14 @@ int make_tmap_2d_f16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
   cuuint64_t strides[1] = {ld * 2};
   cuuint32_t box[2] = {box_cols, box_rows};
   return encode(out, base, 2, dims, strides, box);
+}
+
+int make_tmap_4d_f16(CUtensorMap* out, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t N, uint64_t ldc,
+                     uint32_t box_w, uint32_t box_h, uint32_t box_n) {
+  cuuint64_t dims[4] = {C, W, H, N};
+  cuuint64_t strides[3] = {ldc * 2, W * ldc * 2, H * W * ldc * 2};
+  cuuint32_t box[4] = {64, box_w, box_h, box_n};
+  return encode(out, base, 4, dims, strides, box);
 }
 
 int make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,

@@ -94,8 +94,14 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           uint8_t* sA = smem + stage * C::STAGE_BYTES;
           uint8_t* sB = sA + C::A_BYTES;
           mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
-          const int ka = p.a_kwrap ? (kb * BK) % p.a_kwrap : kb * BK;
-          tma_load_2d(sA, &tmA, &full[stage], ka, m_blk * BM);
+          if (p.conv_taps) {      // implicit convolution: the A tile is a shifted box of the channels-last image
+            int c0, x, y, n;
+            conv_coords(p, kb, m_blk * BM, c0, x, y, n);
+            tma_load_4d(sA, &tmA, &full[stage], c0, x, y, n);
+          } else {
+            const int ka = p.a_kwrap ? (kb * BK) % p.a_kwrap : kb * BK;
+            tma_load_2d(sA, &tmA, &full[stage], ka, m_blk * BM);
+          }
           tma_load_2d(sB, &tmB, &full[stage], kb * BK, n_blk * BN);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -207,7 +213,19 @@ int launch_gemm_f16(cudaStream_t st, const __half* A, int lda, const __half* W, 
   CUtensorMap tmA, tmB;
   const int a_cols = ep.a_kwrap > 0 ? ep.a_kwrap : K;
   BG_REQUIRE(ep.a_kwrap == 0 || (ep.a_kwrap % BK == 0 && ep.a_kwrap <= K), "gemm: a_kwrap must be a multiple of 64");
-  BG_TRY(make_tmap_2d_f16(&tmA, A, (uint64_t)M, (uint64_t)a_cols, (uint64_t)lda, BM));
+  const ConvGeom& cg = ep.conv;
+  if (cg.taps > 0) {
+    const int hw = cg.W * cg.H;
+    BG_REQUIRE(cg.C > 0 && cg.C % 64 == 0 && cg.W > 0 && cg.H > 0 && cg.N > 0 && cg.kw > 0 && cg.taps % cg.kw == 0,
+               "conv gemm: bad geometry");
+    BG_REQUIRE(128 % cg.W == 0 && (hw % 128 == 0 || 128 % hw == 0), "conv gemm: W * H must divide 128 or be a multiple of it");
+    BG_REQUIRE(M == cg.N * hw && K == cg.terms * cg.taps * cg.C && ep.a_kwrap == 0, "conv gemm: M / K do not match the geometry");
+    BG_REQUIRE(lda >= (cg.lo_plane ? 2 : 1) * cg.C, "conv gemm: channel pitch too small");
+    const int box_h = hw >= 128 ? 128 / cg.W : cg.H, box_n = hw >= 128 ? 1 : 128 / hw;
+    BG_TRY(make_tmap_4d_f16(&tmA, A, (uint64_t)(cg.lo_plane ? 2 : 1) * cg.C, cg.W, cg.H, cg.N, (uint64_t)lda, cg.W, box_h, box_n));
+  } else {
+    BG_TRY(make_tmap_2d_f16(&tmA, A, (uint64_t)M, (uint64_t)a_cols, (uint64_t)lda, BM));
+  }
   BG_TRY(make_tmap_2d_f16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, use2 ? 128u : (uint32_t)bn));
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.a_kwrap = ep.a_kwrap; p.m_dev = ep.m_dev; p.row_map = ep.row_map;
@@ -217,6 +235,9 @@ int launch_gemm_f16(cudaStream_t st, const __half* A, int lda, const __half* W, 
   p.out = ep.out; p.ldo = ep.ldo; p.out_f16 = ep.out_f16; p.relu = ep.relu;
   p.bias = ep.bias; p.resid = ep.resid; p.ldr = ep.ldr;
   p.rowvec = ep.rowvec; p.rows_per_vec = ep.rows_per_vec; p.ldv = ep.ldv;
+  p.conv_taps = cg.taps; p.conv_kw = cg.kw; p.conv_cpb = cg.C / 64; p.conv_C = cg.C; p.conv_W = cg.W; p.conv_HW = cg.W * cg.H;
+  p.conv_pad_w = cg.kw / 2; p.conv_pad_h = cg.taps > 0 ? (cg.taps / cg.kw) / 2 : 0;
+  p.conv_lo_term = (cg.taps > 0 && cg.lo_plane && cg.terms == 3) ? 1 : -1;
   if (use2) return launch_gemm2_f16(st, tmA, tmB, p);
   return bn == 256 ? launch_bn<256>(st, tmA, tmB, p) : launch_bn<128>(st, tmA, tmB, p);
 }

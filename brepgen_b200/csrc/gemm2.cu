@@ -87,6 +87,12 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMa
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d_2sm(void* smem_dst, const CUtensorMap* m, uint32_t leader_bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void umma_f16_ss_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -173,8 +179,14 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint8_t* sB = sA + A_BYTES;
           const uint32_t leader_full = smem_u32(&full[stage]) & PEER_MASK;
           if (leader) mbar_arrive_expect_tx(&full[stage], 2 * STAGE_BYTES);
-          const int ka = p.a_kwrap ? (kb * BK) % p.a_kwrap : kb * BK;
-          tma_load_2d_2sm(sA, &tmA, leader_full, ka, m_blk * 2 * BM_CTA + (int)rank * BM_CTA);
+          if (p.conv_taps) {      // implicit convolution: this CTA's 128 output pixels, box shifted by the tap
+            int c0, x, y, n;
+            conv_coords(p, kb, m_blk * 2 * BM_CTA + (int)rank * BM_CTA, c0, x, y, n);
+            tma_load_4d_2sm(sA, &tmA, leader_full, c0, x, y, n);
+          } else {
+            const int ka = p.a_kwrap ? (kb * BK) % p.a_kwrap : kb * BK;
+            tma_load_2d_2sm(sA, &tmA, leader_full, ka, m_blk * 2 * BM_CTA + (int)rank * BM_CTA);
+          }
           tma_load_2d_2sm(sB, &tmB, leader_full, kb * BK, n_blk * BN + (int)rank * (BN / 2));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }

@@ -21,7 +21,20 @@ struct GemmParams {
   int n_short, k_short; // column tiles with n0 < n_short run only k_short / 64 k-blocks (partly split weight matrix)
   const int* m_dev;     // optional device int: the kernels work on min(M, *m_dev) rows (token compaction)
   const int* row_map;   // optional: rowvec row = row_map[row] / rows_per_vec
+  // implicit-GEMM convolution (conv_taps > 0): see ConvGeom in bg_internal.h
+  int conv_taps, conv_kw, conv_cpb /* C / 64 */, conv_C, conv_W, conv_HW, conv_pad_w, conv_pad_h, conv_lo_term;
 };
+
+// coordinates of the A box of k-block kb for the tile whose first row (output pixel) is row0: {channel, x, y, image}
+__device__ __forceinline__ void conv_coords(const GemmParams& p, int kb, int row0, int& c0, int& x, int& y, int& n) {
+  const int per_term = p.conv_taps * p.conv_cpb;
+  const int term = kb / per_term, r = kb - term * per_term;
+  const int tap = r / p.conv_cpb, cc = r - tap * p.conv_cpb;
+  c0 = (term == p.conv_lo_term ? p.conv_C : 0) + cc * 64;
+  x = tap % p.conv_kw - p.conv_pad_w;
+  n = row0 / p.conv_HW;
+  y = (row0 - n * p.conv_HW) / p.conv_W + tap / p.conv_kw - p.conv_pad_h;
+}
 
 // the kernels' working copy of the parameters with the row count resolved on the device
 __device__ __forceinline__ GemmParams gemm_resolve(const GemmParams& p) {

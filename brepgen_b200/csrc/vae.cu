@@ -5,11 +5,13 @@
 // UpBlock1D :30-48, cfg sample.py:86-97); layer-by-layer arithmetic: SURVEY.md Appendix A.1 / A.2.
 //
 // Layout: activations are channels-last ([sample][position][channel]), fp32 for the residual stream and fp16 for GEMM
-// operands.  Every convolution is an im2col gather (fp16, nearest-2x upsampling folded into the gather) followed by the
-// tcgen05 GEMM of gemm.cu, whose epilogue adds bias and the residual; GroupNorm + SiLU/GELU (+ residual) is one
-// CTA-per-sample kernel; the tiny attentions (16 tokens x 512 / 4 tokens x 16 heads x 32) run on CUDA cores.
-// Decode is ~0.13 % of the cascade's FLOPs, so the explicit im2col (HBM-bound, ~9x activation traffic) is
-// accepted here; the GEMMs are tensor-bound.
+// operands.  Convolutions are IMPLICIT GEMMs on the tcgen05 GEMM kernels (gemm.cu / gemm2.cu, ConvGeom): the A tile of
+// k-block (term, tap, 64-channel chunk) is a TMA box of the channels-last image shifted by the tap's offset, out-of-range
+// coordinates zero-filled = the padding, so the im2col matrix only ever exists as shared-memory tiles (round 1 / early
+// round 2 materialised it in HBM: ~9x the activation traffic and ~40 % of the decode time).  The few shapes a box cannot
+// express (3 input channels, 3 x 3 / 24 x 24 extents, stride-2 encoder convolutions) keep the explicit gather.  The GEMM
+// epilogue adds bias and the residual; GroupNorm + SiLU/GELU (+ residual) is one CTA-per-sample kernel; nearest-2x
+// upsampling is one gather into the next convolution's input; the tiny attentions run on CUDA cores.
 #include <map>
 #include <string>
 #include <vector>
@@ -80,6 +82,17 @@ __global__ void cast_split_kernel(const float* __restrict__ x, __half* __restric
     const size_t row = i / C;
     const int c = (int)(i % C);
     store_hl(y + row * 2 * C + c, C, x[i]);
+  }
+}
+
+// nearest-2x upsampling into the [hi | lo] fp16 input of the following convolution: x fp32 (N, H, W, C) -> y (N, 2H, 2W, 2C)
+__global__ void upsample2x_split_kernel(const float* __restrict__ x, __half* __restrict__ y, int H, int W, int C, size_t total) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    size_t pix = i / C;                                   // output pixel (n, yo, xo)
+    const int xo = (int)(pix % (2 * W)), yo = (int)((pix / (2 * W)) % (2 * H));
+    const size_t n = pix / ((size_t)4 * W * H);
+    store_hl(y + pix * 2 * C + c, C, x[((n * H + (yo >> 1)) * W + (xo >> 1)) * C + c]);
   }
 }
 
@@ -211,6 +224,59 @@ __global__ void groupnorm_kernel(const float* __restrict__ x, int ldx, int P, in
   const float ga = gamma[c] * rstd, be = beta[c] - mean * gamma[c] * rstd;
   for (int p = 0; p < P; ++p) {
     float y = act_fn(xs[(size_t)p * ldx + c] * ga + be, act);
+    const size_t o = ((size_t)n * P + p) * C + c;
+    if (resid) y += resid[o];
+    if (out32) out32[o] = y;
+    if (out16) store_hl(out16 + ((size_t)n * P + p) * 2 * C + c, C, y);
+  }
+}
+
+// Same for P <= 64 positions (every 1-D stage, the 4x4 / 8x8 2-D stages): the thread's P values stay in registers, so the
+// activation is read once instead of three times (this kernel was 30 % of the edge decoder).
+template <int P>
+__global__ void groupnorm_regs_kernel(const float* __restrict__ x, int ldx, int C, int G, float eps,
+                                      const float* __restrict__ gamma, const float* __restrict__ beta, int act,
+                                      const float* __restrict__ resid, float* __restrict__ out32, __half* __restrict__ out16) {
+  __shared__ float s_part[32];
+  const int n = blockIdx.x, c = threadIdx.x;
+  const int cpg = C / G;
+  const float* xs = x + (size_t)n * P * ldx;
+  const int lane = c & 31, warp = c >> 5;
+  const float cnt = (float)P * cpg;
+  auto group_reduce = [&](float v) -> float {
+    if (cpg <= 32) {
+      for (int o = cpg >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      return v;
+    }
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if (lane == 0) s_part[warp] = v;
+    __syncthreads();
+    const int wpg = cpg >> 5;
+    float t = 0.f;
+    const int w0 = (warp / wpg) * wpg;
+    for (int w = 0; w < wpg; ++w) t += s_part[w0 + w];
+    return t;
+  };
+  float v[P];
+  float s = 0.f;
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    v[p] = xs[(size_t)p * ldx + c];
+    s += v[p];
+  }
+  const float mean = group_reduce(s) / cnt;
+  float q = 0.f;
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    const float d = v[p] - mean;
+    q += d * d;
+  }
+  const float rstd = rsqrtf(group_reduce(q) / cnt + eps);
+  const float ga = gamma[c] * rstd, be = beta[c] - mean * gamma[c] * rstd;
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    float y = act_fn(v[p] * ga + be, act);
     const size_t o = ((size_t)n * P + p) * C + c;
     if (resid) y += resid[o];
     if (out32) out32[o] = y;
@@ -659,9 +725,37 @@ int gemm(const Ctx& c, const __half* A, const Conv& cv, size_t rows, float* out3
   ep.a_kwrap = cv.kpad;          // [A_hi | A_hi] x [W_hi | W_lo]  (the lo plane of A is not read)
   return launch_gemm_f16(c.st, A, 2 * cv.kpad, cv.w, 3 * cv.kpad, (int)rows, cv.cout_pad, 2 * cv.kpad, ep);
 }
+// shapes the implicit convolution covers: a 128-row tile of output pixels must be a box {W, box_h, box_n} of whole image rows
+bool conv_implicit_ok(int H, int W, int C) {
+  const int hw = H * W;
+  return C % 64 == 0 && W <= 128 && 128 % W == 0 && (hw % 128 == 0 || 128 % hw == 0);
+}
+// stride-1 "same" convolution (taps = kh * kw) of the [hi | lo] fp16 image `in` (N, H, W, 2 * cv.cin) as an implicit GEMM
+int conv_gemm(const Ctx& c, const __half* in, int H, int W, int taps, int kw, const Conv& cv, float* out32, __half* out16,
+              const float* resid) {
+  GemmEpilogue ep;
+  ep.out = out16 ? (void*)out16 : (void*)out32;
+  ep.out_f16 = out16 ? 1 : 0;
+  ep.ldo = cv.cout_pad;
+  ep.bias = cv.bias;
+  ep.resid = resid;
+  ep.ldr = cv.cout_pad;
+  ep.conv.taps = taps; ep.conv.kw = kw; ep.conv.C = cv.cin; ep.conv.W = W; ep.conv.H = H; ep.conv.N = (int)c.N;
+  ep.conv.lo_plane = 1; ep.conv.terms = c.terms;
+  return launch_gemm_f16(c.st, in, 2 * cv.cin, cv.w, 3 * cv.kpad, (int)(c.N * H * W), cv.cout_pad, c.terms * cv.kpad, ep);
+}
 int groupnorm(const Ctx& c, const float* x, int P, int C, int G, float eps, const Norm& n, int act, const float* resid,
               float* out32, __half* out16) {
-  groupnorm_kernel<<<(unsigned)c.N, C, 0, c.st>>>(x, C, P, C, G, eps, n.g, n.b, act, resid, out32, out16);
+  switch (P) {
+#define BG_GN_CASE(PP)                                                                                                   \
+    case PP:                                                                                                             \
+      groupnorm_regs_kernel<PP><<<(unsigned)c.N, C, 0, c.st>>>(x, C, C, G, eps, n.g, n.b, act, resid, out32, out16);     \
+      break;
+    BG_GN_CASE(4) BG_GN_CASE(8) BG_GN_CASE(16) BG_GN_CASE(32) BG_GN_CASE(64)
+#undef BG_GN_CASE
+    default:
+      groupnorm_kernel<<<(unsigned)c.N, C, 0, c.st>>>(x, C, P, C, G, eps, n.g, n.b, act, resid, out32, out16);
+  }
   return check_launch("groupnorm_kernel launch");
 }
 int cast_split(const Ctx& c, const float* x, __half* y, int C, size_t rows) {
@@ -688,6 +782,16 @@ int im2col1d(const Ctx& c, const __half* in, int L, int C, int ks, int kpad) {
   }
   return BG_OK;
 }
+int conv3x3(const Ctx& c, const __half* in, int H, const Conv& cv, float* out32, const float* resid) {
+  if (conv_implicit_ok(H, H, cv.cin)) return conv_gemm(c, in, H, H, 9, 3, cv, out32, nullptr, resid);
+  BG_TRY(im2col2d(c, in, H, H, cv.cin, 1, cv.kpad));
+  return gemm(c, c.w.A, cv, c.N * H * H, out32, nullptr, resid);
+}
+int conv1d(const Ctx& c, const __half* in, int L, int ks, const Conv& cv, float* out32, const float* resid) {
+  if (conv_implicit_ok(1, L, cv.cin)) return conv_gemm(c, in, 1, L, ks, ks, cv, out32, nullptr, resid);
+  BG_TRY(im2col1d(c, in, L, cv.cin, ks, cv.kpad));
+  return gemm(c, c.w.A, cv, c.N * L, out32, nullptr, resid);
+}
 int attention(const Ctx& c, int T, int Hh, int dh, float scale) {
   const int C = Hh * dh;
   const size_t smem = (size_t)(3 * T * C + Hh * T * T) * 4;
@@ -701,16 +805,17 @@ int resnet2d(const Ctx& c, const Res2d& r, float** px, float** pfree, int HW, in
   const int cin = r.c1.cin, cout = r.c1.cout;
   float* x = *px;
   BG_TRY(groupnorm(c, x, HW, cin, 32, 1e-6f, r.n1, 1, nullptr, nullptr, c.w.T));
-  BG_TRY(im2col2d(c, c.w.T, H, H, cin, 1, r.c1.kpad));
-  BG_TRY(gemm(c, c.w.A, r.c1, c.N * HW, c.w.H, nullptr, nullptr));
-  BG_TRY(groupnorm(c, c.w.H, HW, cout, 32, 1e-6f, r.n2, 1, nullptr, nullptr, c.w.T));
-  BG_TRY(im2col2d(c, c.w.T, H, H, cout, 1, r.c2.kpad));
-  if (!r.has_sc) return gemm(c, c.w.A, r.c2, c.N * HW, x, nullptr, x);
-  // 1x1 shortcut on the raw input, then conv2 accumulates onto it
+  BG_TRY(conv3x3(c, c.w.T, H, r.c1, c.w.H, nullptr));
+  if (!r.has_sc) {
+    BG_TRY(groupnorm(c, c.w.H, HW, cout, 32, 1e-6f, r.n2, 1, nullptr, nullptr, c.w.T));
+    return conv3x3(c, c.w.T, H, r.c2, x, x);
+  }
+  // 1x1 shortcut on the raw input (T is free between the two convolutions), then conv2 accumulates onto it
   float* s = *pfree;
-  BG_TRY(cast_split(c, x, c.w.T, cin, c.N * (size_t)HW));   // T is free again: A already holds conv2's im2col
+  BG_TRY(cast_split(c, x, c.w.T, cin, c.N * (size_t)HW));
   BG_TRY(gemm(c, c.w.T, r.sc, c.N * HW, s, nullptr, nullptr));
-  BG_TRY(gemm(c, c.w.A, r.c2, c.N * HW, s, nullptr, s));
+  BG_TRY(groupnorm(c, c.w.H, HW, cout, 32, 1e-6f, r.n2, 1, nullptr, nullptr, c.w.T));
+  BG_TRY(conv3x3(c, c.w.T, H, r.c2, s, s));
   *px = s;
   *pfree = x;
   return BG_OK;
@@ -727,11 +832,9 @@ int resconv1d(const Ctx& c, const Res1d& r, float** px, float** pfree, int L) {
     res = *pfree;
     out = *pfree;
   }
-  BG_TRY(im2col1d(c, c.w.T, L, cin, 5, r.c1.kpad));
-  BG_TRY(gemm(c, c.w.A, r.c1, c.N * L, c.w.H, nullptr, nullptr));
+  BG_TRY(conv1d(c, c.w.T, L, 5, r.c1, c.w.H, nullptr));
   BG_TRY(groupnorm(c, c.w.H, L, cmid, 1, 1e-5f, r.n1, 2, nullptr, nullptr, c.w.T));
-  BG_TRY(im2col1d(c, c.w.T, L, cmid, 5, r.c2.kpad));
-  BG_TRY(gemm(c, c.w.A, r.c2, c.N * L, c.w.H, nullptr, nullptr));
+  BG_TRY(conv1d(c, c.w.T, L, 5, r.c2, c.w.H, nullptr));
   BG_TRY(groupnorm(c, c.w.H, L, cout, 1, 1e-5f, r.n2, 2, res, out, nullptr));
   if (r.has_skip) {
     *px = out;
@@ -820,16 +923,23 @@ int bg_vae_decode_hw(BgVae* m, const float* z, int N, int hw, float* out, void* 
       for (int j = 0; j < 3; ++j) BG_TRY(resnet2d(c, m->s_up[i][j], &x, &spare, H * H, H));
       if (i < 3) {
         const Conv& uc = m->s_upconv[i];
-        BG_TRY(cast_split(c, x, c.w.T, uc.cin, c.N * (size_t)H * H));
-        BG_TRY(im2col2d(c, c.w.T, H, H, uc.cin, 2, uc.kpad));
-        H *= 2;
-        BG_TRY(gemm(c, c.w.A, uc, c.N * H * H, spare, nullptr, nullptr));
+        if (conv_implicit_ok(2 * H, 2 * H, uc.cin)) {      // nearest 2x into the convolution's input, then implicit GEMM
+          const size_t tot = c.N * (size_t)4 * H * H * uc.cin;
+          upsample2x_split_kernel<<<grid_for(tot), 256, 0, c.st>>>(x, c.w.T, H, H, uc.cin, tot);
+          BG_TRY(check_launch("upsample2x_split_kernel launch"));
+          H *= 2;
+          BG_TRY(conv_gemm(c, c.w.T, H, H, 9, 3, uc, spare, nullptr, nullptr));
+        } else {
+          BG_TRY(cast_split(c, x, c.w.T, uc.cin, c.N * (size_t)H * H));
+          BG_TRY(im2col2d(c, c.w.T, H, H, uc.cin, 2, uc.kpad));
+          H *= 2;
+          BG_TRY(gemm(c, c.w.A, uc, c.N * H * H, spare, nullptr, nullptr));
+        }
         float* t = x; x = spare; spare = t;
       }
     }
     BG_TRY(groupnorm(c, x, H * H, 128, 32, 1e-6f, m->norm_out, 1, nullptr, nullptr, c.w.T));
-    BG_TRY(im2col2d(c, c.w.T, H, H, 128, 1, m->conv_out.kpad));
-    BG_TRY(gemm(c, c.w.A, m->conv_out, c.N * H * H, c.w.H, nullptr, nullptr));
+    BG_TRY(conv3x3(c, c.w.T, H, m->conv_out, c.w.H, nullptr));
     slice_out_kernel<<<(N * 3 * H * H + 255) / 256, 256, 0, c.st>>>(c.w.H, 128, out, N, H * H);
     return check_launch("slice_out_kernel launch");
   }
@@ -857,8 +967,7 @@ int bg_vae_decode_hw(BgVae* m, const float* z, int N, int hw, float* out, void* 
     L *= 2;
   }
   BG_TRY(groupnorm(c, x, 32, 128, 32, 1e-6f, m->norm_out, 1, nullptr, nullptr, c.w.T));
-  BG_TRY(im2col1d(c, c.w.T, 32, 128, 3, m->conv_out.kpad));
-  BG_TRY(gemm(c, c.w.A, m->conv_out, c.N * 32, c.w.H, nullptr, nullptr));
+  BG_TRY(conv1d(c, c.w.T, 32, 3, m->conv_out, c.w.H, nullptr));
   slice_out_kernel<<<(N * 3 * 32 + 255) / 256, 256, 0, c.st>>>(c.w.H, 128, out, N, 32);
   return check_launch("slice_out_kernel launch");
 }
