@@ -4,7 +4,8 @@
 without conv_shortcut), `_attn2d` and `_upsample2d` reproduce the expected output slices of diffusers'
 tests/models/test_layers_utils.py (ResnetBlock2DTests.test_resnet_default / test_restnet_with_use_in_shortcut,
 AttentionBlockTests.test_attention_block_default, Upsample2DBlockTests.test_upsample_default / test_upsample_with_conv) to 4
-decimals.  1-D leaves (ResConvBlock, SelfAttention1d, Upsample1d; diffusers has no known-answer test for them) and the 2-D
+decimals, and the block wiring (resnet -> upsample; resnet -> attention -> resnet) those of test_unet_2d_blocks.py
+(UpDecoderBlock2DTests / UNetMidBlock2DTests).  1-D leaves (ResConvBlock, SelfAttention1d, Upsample1d; diffusers has no known-answer test for them) and the 2-D
 encoder's Downsample2D remain PARITY UNPINNED.  The arithmetic lives in diffusers==0.27 (requirements.txt:5 of the reference), which is absent from
 /root/reference and from this image: `Decoder`, `UNetMidBlock2D`, `UpDecoderBlock2D`, `ResnetBlock2D`, `Attention`,
 `Upsample2D` (surface) and `ResConvBlock`, `SelfAttention1d`, `Upsample1d` (edge).  This file restates their published

@@ -62,3 +62,34 @@ def test_upsample_with_conv():            # Upsample2DBlockTests.test_upsample_w
         out = V._upsample2d(sd, "u", sample)
     assert out.shape == (1, 32, 64, 64)
     _check(out, [0.7145, 1.3773, 0.3492, 0.8448, 1.0839, -0.3341, 0.5956, 0.1250, -0.4841])
+
+
+# ---- block level (diffusers tests/models/unets/test_unet_2d_blocks.py over test_unet_blocks_common.py: torch.manual_seed(0),
+# hidden_states randn(4, 32, 32, 32) [, temb randn(4, 128)], THEN the block is constructed from the same generator)
+def test_up_decoder_block():              # UpDecoderBlock2DTests.test_output: ResnetBlock2D (no time embedding) -> Upsample2D(conv)
+    torch.manual_seed(0)
+    x = torch.randn(4, 32, 32, 32)
+    c1, c2, up = nn.Conv2d(32, 32, 3, padding=1), nn.Conv2d(32, 32, 3, padding=1), nn.Conv2d(32, 32, 3, padding=1)
+    sd = {**_gn("r.norm1", 32), **_gn("r.norm2", 32), **_conv("r.conv1", c1), **_conv("r.conv2", c2), **_conv("u.conv", up)}
+    with torch.no_grad():
+        out = V._upsample2d(sd, "u", V._resnet2d(sd, "r", x))       # exactly the VAE decoder's up block (temb is None there)
+    assert out.shape == (4, 32, 64, 64)
+    _check(out, [0.4404, 0.1998, -0.9886, -0.3320, -0.3128, -0.7034, -0.6955, -0.2338, -0.3137])
+
+
+def test_unet_mid_block():                # UNetMidBlock2DTests.test_output: resnet -> attention (heads of dimension 1) -> resnet
+    torch.manual_seed(0)
+    x, temb = torch.randn(4, 32, 32, 32), torch.randn(4, 128)
+    mk = lambda: (nn.Conv2d(32, 32, 3, padding=1), nn.Linear(128, 32), nn.Conv2d(32, 32, 3, padding=1))
+    r0 = mk()                             # UNetMidBlock2D.__init__: resnets[0], attentions[0], resnets[1]
+    q, k, v, o = (nn.Linear(32, 32) for _ in range(4))
+    r1 = mk()
+    sd = {**_gn("a.group_norm", 32), **_conv("a.to_q", q), **_conv("a.to_k", k), **_conv("a.to_v", v), **_conv("a.to_out.0", o)}
+    for name, (c1, _, c2) in (("r0", r0), ("r1", r1)):
+        sd.update({**_gn(name + ".norm1", 32), **_gn(name + ".norm2", 32), **_conv(name + ".conv1", c1), **_conv(name + ".conv2", c2)})
+    silu = torch.nn.functional.silu
+    with torch.no_grad():
+        y = V._resnet2d(sd, "r0", x, temb_add=r0[1](silu(temb))[:, :, None, None])
+        y = V._attn2d(sd, "a", y, n_head=32)
+        y = V._resnet2d(sd, "r1", y, temb_add=r1[1](silu(temb))[:, :, None, None])
+    _check(y, [-0.1062, 1.7248, 0.3494, 1.4569, -0.0910, -1.2421, -0.9984, 0.6736, 1.0028])
