@@ -424,6 +424,7 @@ using namespace bg;
 struct BgVae {
   int kind = 0;                 // 0 surface decoder, 1 edge decoder, 2 surface encoder, 3 edge encoder
   int terms = 3;                // product terms of the compensated GEMMs (vae_terms_for)
+  int implicit = 1;             // convolutions as implicit GEMMs; BREPGEN_B200_VAE_IM2COL=1 at creation: explicit gather (A/B)
   char* arena = nullptr;
   size_t arena_bytes = 0;
   float *pq_w = nullptr, *pq_b = nullptr, *up_kernel = nullptr;
@@ -707,6 +708,7 @@ struct Ctx {
   size_t N;
   VaeWs w;
   int terms = 3;
+  int implicit = 1;
 };
 
 // A: [rows][2 * cv.kpad] fp16 = [A_hi | A_lo]
@@ -783,12 +785,12 @@ int im2col1d(const Ctx& c, const __half* in, int L, int C, int ks, int kpad) {
   return BG_OK;
 }
 int conv3x3(const Ctx& c, const __half* in, int H, const Conv& cv, float* out32, const float* resid) {
-  if (conv_implicit_ok(H, H, cv.cin)) return conv_gemm(c, in, H, H, 9, 3, cv, out32, nullptr, resid);
+  if (c.implicit && conv_implicit_ok(H, H, cv.cin)) return conv_gemm(c, in, H, H, 9, 3, cv, out32, nullptr, resid);
   BG_TRY(im2col2d(c, in, H, H, cv.cin, 1, cv.kpad));
   return gemm(c, c.w.A, cv, c.N * H * H, out32, nullptr, resid);
 }
 int conv1d(const Ctx& c, const __half* in, int L, int ks, const Conv& cv, float* out32, const float* resid) {
-  if (conv_implicit_ok(1, L, cv.cin)) return conv_gemm(c, in, 1, L, ks, ks, cv, out32, nullptr, resid);
+  if (c.implicit && conv_implicit_ok(1, L, cv.cin)) return conv_gemm(c, in, 1, L, ks, ks, cv, out32, nullptr, resid);
   BG_TRY(im2col1d(c, in, L, cv.cin, ks, cv.kpad));
   return gemm(c, c.w.A, cv, c.N * L, out32, nullptr, resid);
 }
@@ -853,6 +855,7 @@ int bg_vae_create(int kind, const BgNamedTensor* weights, int n_weights, void* s
   BgVae* m = new BgVae();
   m->kind = kind;
   m->terms = vae_terms_for(kind);
+  if (const char* e = getenv("BREPGEN_B200_VAE_IM2COL")) m->implicit = atoi(e) ? 0 : 1;
   VPacker pk;
   pk.terms = m->terms;
   for (int i = 0; i < n_weights; ++i) pk.by_name[weights[i].name] = &weights[i];
@@ -897,6 +900,7 @@ int bg_vae_decode_hw(BgVae* m, const float* z, int N, int hw, float* out, void* 
   c.st = reinterpret_cast<cudaStream_t>(stream);
   c.N = (size_t)N;
   c.terms = m->terms;
+  c.implicit = m->implicit;
   char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
   c.w = carve_vae(base, m->kind, c.N);
   if (c.w.bytes + (size_t)(base - reinterpret_cast<char*>(workspace)) > workspace_bytes)
@@ -923,7 +927,7 @@ int bg_vae_decode_hw(BgVae* m, const float* z, int N, int hw, float* out, void* 
       for (int j = 0; j < 3; ++j) BG_TRY(resnet2d(c, m->s_up[i][j], &x, &spare, H * H, H));
       if (i < 3) {
         const Conv& uc = m->s_upconv[i];
-        if (conv_implicit_ok(2 * H, 2 * H, uc.cin)) {      // nearest 2x into the convolution's input, then implicit GEMM
+        if (c.implicit && conv_implicit_ok(2 * H, 2 * H, uc.cin)) {      // nearest 2x into the convolution's input, then implicit GEMM
           const size_t tot = c.N * (size_t)4 * H * H * uc.cin;
           upsample2x_split_kernel<<<grid_for(tot), 256, 0, c.st>>>(x, c.w.T, H, H, uc.cin, tot);
           BG_TRY(check_launch("upsample2x_split_kernel launch"));
@@ -981,6 +985,7 @@ int bg_vae_encode(BgVae* m, const float* xin, int N, int hw, float* out, void* w
   c.st = reinterpret_cast<cudaStream_t>(stream);
   c.N = (size_t)N;
   c.terms = m->terms;
+  c.implicit = m->implicit;
   char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
   c.w = carve_vae(base, m->kind, c.N);
   if (c.w.bytes + (size_t)(base - reinterpret_cast<char*>(workspace)) > workspace_bytes)

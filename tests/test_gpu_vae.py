@@ -174,3 +174,26 @@ def test_decoders_graph_replay_equals_eager():
     torch.cuda.synchronize()
     assert len(sv._graphs) == 1 and len(ev._graphs) == 1
     assert torch.equal(a_s, b_s) and torch.equal(a_e, b_e) and torch.equal(b_s, c_s)
+
+
+def test_implicit_convolutions_equal_explicit_im2col():
+    """the implicit-GEMM convolutions (TMA boxes of the image per tap) and the explicit im2col gather + GEMM run the same
+    k-block order through the same MMA, so the decoders' outputs are bit-identical; the switch is read at handle creation"""
+    import os
+    from brepgen_b200.vae import build_synthetic_decoders
+    dev = torch.device("cuda")
+    zs = torch.randn(37, 3, 4, 4, generator=torch.Generator().manual_seed(3)).cuda()      # 37 * 16 rows: a ragged last tile
+    ze = torch.randn(203, 3, 4, generator=torch.Generator().manual_seed(4)).cuda()
+    outs = []
+    for explicit in (0, 1):
+        os.environ["BREPGEN_B200_VAE_IM2COL"] = str(explicit)
+        try:
+            sv, ev = build_synthetic_decoders(dev)
+            sv.use_graph = ev.use_graph = False
+            with torch.no_grad():
+                outs.append((sv(zs), ev(ze)))
+            torch.cuda.synchronize()
+        finally:
+            os.environ.pop("BREPGEN_B200_VAE_IM2COL", None)
+    assert torch.isfinite(outs[0][0]).all() and torch.isfinite(outs[0][1]).all()
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
