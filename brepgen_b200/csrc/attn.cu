@@ -87,8 +87,10 @@ __device__ long long g_attn_trace[2][64][8];
 #define BG_TR(pt)
 #endif
 
-// PM: 4-bit mask over the 4 element pairs of each 8-key chunk whose exp2 runs as a polynomial on the FMA pipe instead of
-// MUFU.EX2 (the XU pipe, 16 ex2/clk/SM, is the binding unit of d=64 attention on B200)
+// PM: which exponentials run as a polynomial on the FMA pipe instead of MUFU.EX2: bit q of the low byte = element pair q
+// (0..7) of the EVEN 16-key groups, of the high byte = of the odd groups (0x8888 = pairs 3 and 7 of every group = 25 %).
+// Dispatch costs measured in profiles/r02_pipe_rates.txt: a polynomial pair ~22 cycles of the sub-partition's dispatch
+// port, two MUFU ~5 (+ 16 cycles of the XU pipe, 16 ex2/clk/SM)
 // PT: P goes to TENSOR MEMORY (tcgen05.st, two fp16 per column) and the PV MMA takes its A operand from TMEM -- per key
 // block this removes 64 KB of shared-memory writes + 64 KB of reads, which otherwise make the kernel smem-bandwidth bound
 // (QK^T and PV operand reads + P + TMA fills = 256 KB per block ~ 2048 cycles at 128 B/clk vs 1024 MMA cycles).
@@ -380,8 +382,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const float2 a = ffma2(make_float2(s[16 * g + 2 * q], s[16 * g + 2 * q + 1]), c2, nmc2);
-          // PM: bits 0-3 = pattern of the even 16-key groups, bits 4-7 = of the odd ones (0 = same as even)
-          e[q] = ((((g & 1) && (PM >> 4)) ? (PM >> 4) : PM) >> (q & 3)) & 1 ? exp2_poly2(a) : make_float2(ex2(a.x), ex2(a.y));
+          // PM: bit q of the low byte = element pair q (0..7) of the even 16-key groups, of the high byte = of the odd groups
+          e[q] = ((PM >> ((g & 1) * 8 + q)) & 1) ? exp2_poly2(a) : make_float2(ex2(a.x), ex2(a.y));
         }
       };
       auto drain_group = [&](int g, const float2 (&e)[8]) {
@@ -531,7 +533,7 @@ int launch_attention(cudaStream_t st, const AttnArgs& a) {
   p.scale_log2 = 1.4426950408889634f / 8.0f;
   static int poly = -1, ptmem = 1, pingpong = 1;   // environment knobs, read once per process
   if (poly < 0) {
-    const char* e = getenv("BG_ATTN_POLY");   // share of the exponentials on the FMA pipe: 0 | 1 (25 %, default) | 2 (50 %) | 3 (37.5 %)
+    const char* e = getenv("BG_ATTN_POLY");   // exponentials on the FMA pipe: 0 | 1 (25 %, default) | 2 (50 %) | 3 (37.5 %)
     poly = e ? atoi(e) : 1;
     e = getenv("BG_ATTN_PT");                 // 0: P through shared memory (the round-1 path, kept as the A/B reference)
     ptmem = e ? atoi(e) : 1;
@@ -542,14 +544,14 @@ int launch_attention(cudaStream_t st, const AttnArgs& a) {
   p.probe = 0;
   if (a.L <= 128) return launch_nt<1, 0, 0>(st, tm, p);
   if (ptmem) {
-    if (poly == 0) return launch_nt<2, 0x0, 1, 1>(st, tm, p);
-    if (poly == 2) return launch_nt<2, 0xA, 1, 1>(st, tm, p);
-    if (poly == 3) return launch_nt<2, 0xA8, 1, 1>(st, tm, p);    // 37.5 %: 25 % in even, 50 % in odd 16-key groups
-    return launch_nt<2, 0x8, 1, 1>(st, tm, p);
+    if (poly == 0) return launch_nt<2, 0x0000, 1, 1>(st, tm, p);
+    if (poly == 2) return launch_nt<2, 0xAAAA, 1, 1>(st, tm, p);
+    if (poly == 3) return launch_nt<2, 0xAA88, 1, 1>(st, tm, p);    // 37.5 %: 25 % in even, 50 % in odd 16-key groups
+    return launch_nt<2, 0x8888, 1, 1>(st, tm, p);
   }
-  if (poly == 0) return launch_nt<2, 0x0, 0, 1>(st, tm, p);
-  if (poly == 2) return launch_nt<2, 0xA, 0, 1>(st, tm, p);
-  return launch_nt<2, 0x8, 0, 1>(st, tm, p);
+  if (poly == 0) return launch_nt<2, 0x0000, 0, 1>(st, tm, p);
+  if (poly == 2) return launch_nt<2, 0xAAAA, 0, 1>(st, tm, p);
+  return launch_nt<2, 0x8888, 0, 1>(st, tm, p);
 }
 
 #ifdef BG_ATTN_TRACE
