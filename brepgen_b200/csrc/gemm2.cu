@@ -20,7 +20,8 @@
 //            (256 KB of residual in + result out per 128 x 256 tile against 2048 tensor cycles): each epilogue warp
 //            TMA-loads the residual 32 x 32 sub-tile into a swizzled staging buffer one chunk ahead, adds accumulator + bias
 //            there and TMA-stores it -- deep asynchronous queues instead of per-warp load / store bursts.  Measured at
-//            M = 256 000 (B = 64): out-proj 665 -> 580 us (4.07 TB/s), FFN2 571 -> 423 us (4.96 TB/s).  4-stage ring.
+//            M = 256 000 (B = 64): out-proj 665 -> 548 us (4.31 TB/s), FFN2 571 -> 426 us (4.93 TB/s).  5-stage ring, two
+//            staging buffers per warp (4 + 3: 569 / 428 us).
 //   RES = 2  fp16 outputs (q|k|v, FFN1): the direct form of RES = 0 writes 64 B per thread into 32 different rows per warp
 //            instruction (32 separate sectors); at K = 768 a tile's main loop is only 6144 cycles and that store pattern paced
 //            the whole kernel (timing experiment without the stores: q|k 602 -> 393 us, FFN1 388 -> 270 us).  Here every
@@ -46,12 +47,16 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES;            // 32 KB per CTA
 constexpr int BAR_BYTES = 256;
 constexpr int XPOSE_BYTES = 8 * 32 * GEMM_XPOSE_PITCH * 4;
 constexpr int SMEM_BYTES = NSTAGES * STAGE_BYTES + BAR_BYTES + XPOSE_BYTES + 1024;
-// RES == 1 (TMA-staged residual epilogue): 4-stage ring, 1 KB of barriers, then 8 warps x 3 buffers of 32 rows x 128 B
+// RES == 1 (TMA-staged residual epilogue): 5-stage ring, 1 KB of barriers, then 8 warps x 2 buffers of 32 rows x 128 B
 // RES == 2 (fp16 TMA-store epilogue): 5-stage ring, two staging buffers per warp
 constexpr int X_BUF_BYTES = 32 * 128;
+#ifndef BG_RES1_STAGES        // measured at M = 256 000: 4 stages + 3 staging buffers 569 us (out-proj) / 428 (FFN2), 5 + 2: 548 / 426
+#define BG_RES1_STAGES 5
+#define BG_RES1_BUFS 2
+#endif
 template <int RES> struct XL {                       // shared-memory layout of the staged-epilogue variants
-  static constexpr int STAGES = RES == 2 ? 5 : 4;
-  static constexpr int BUFS = RES == 2 ? 2 : 3;
+  static constexpr int STAGES = RES == 2 ? 5 : BG_RES1_STAGES;
+  static constexpr int BUFS = RES == 2 ? 2 : BG_RES1_BUFS;
   static constexpr int OFF_BAR = STAGES * STAGE_BYTES;
   static constexpr int OFF_STG = OFF_BAR + 1024;
   static constexpr int SMEM_BYTES = OFF_STG + 8 * BUFS * X_BUF_BYTES + 1024;
@@ -242,7 +247,7 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // residual chunk c+1 is loaded (TMA, swizzled rows) while chunk c is combined in shared memory and stored (TMA):
         // the memory system sees deep asynchronous queues instead of per-warp load / store bursts
         auto issue_load = [&](uint32_t qq, int c) {      // lane 0 only
-          bulk_wait_read<1>();                           // the store that last read buffer qq % 3 (two chunks ago) is done with it
+          bulk_wait_read<X_BUFS - 2>();                  // the store that last read buffer qq % BUFS is done with it
           const uint32_t b = qq % X_BUFS;
           mbar_arrive_expect_tx(&xbar[b], X_BUF_BYTES);
           tma_load_2d(xstg + b * X_BUF_BYTES, &em.x, &xbar[b], colbase + c * 32, row0);
