@@ -205,7 +205,8 @@ int launch_gemm_f16(cudaStream_t st, const __half* A, int lda, const __half* W, 
   // is the latency of ONE tile's serial main loop -- 128 x 128 tiles on single CTAs give 4x as many tiles with a 4x shorter
   // main loop each.
   int bn = (N % 256 == 0) ? 256 : 128;
-  bool use2 = two_cta && bn == 256;
+  // N % 256 != 0 (the Cout = 128 convolutions of the VAEs): 256 x 128 tiles on CTA pairs when there are enough of them
+  bool use2 = two_cta && (bn == 256 || (long long)((M + 255) / 256) * (N / 128) >= num_sms());
   if (small_m && bn == 256 && (long long)((M + 255) / 256) * (N / 256) < num_sms() / 2) {
     bn = 128;
     use2 = false;
@@ -226,7 +227,7 @@ int launch_gemm_f16(cudaStream_t st, const __half* A, int lda, const __half* W, 
   } else {
     BG_TRY(make_tmap_2d_f16(&tmA, A, (uint64_t)M, (uint64_t)a_cols, (uint64_t)lda, BM));
   }
-  BG_TRY(make_tmap_2d_f16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, use2 ? 128u : (uint32_t)bn));
+  BG_TRY(make_tmap_2d_f16(&tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, use2 ? (uint32_t)bn / 2 : (uint32_t)bn));
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.a_kwrap = ep.a_kwrap; p.m_dev = ep.m_dev; p.row_map = ep.row_map;
   p.n_short = ep.n_short; p.k_short = ep.k_short;

@@ -38,15 +38,19 @@ namespace bg {
 namespace {
 
 constexpr int BM_CTA = 128;     // rows per CTA; the pair covers 256
-constexpr int BN = 256;
 constexpr int BK = 64;
 constexpr int NSTAGES = 6;
 constexpr int A_BYTES = BM_CTA * BK * 2;
-constexpr int B_BYTES = (BN / 2) * BK * 2;
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;            // 32 KB per CTA
+// BN = 256 (default) or 128 (N % 256 != 0: the Cout = 128 convolutions of the VAEs -- a 1-CTA 128 x 128 tile reads 32 KB
+// of shared memory per 256 tensor cycles and sits at ~37 % tensor-pipe activity; the pair's 256 x 128 tile reads 24 KB)
+template <int BN> struct TL {
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;   // 32 KB (BN = 256) / 24 KB (BN = 128) per CTA
+  static constexpr int TMEM_COLS = 2 * BN;                // accumulator double buffer
+};
 constexpr int BAR_BYTES = 256;
 constexpr int XPOSE_BYTES = 8 * 32 * GEMM_XPOSE_PITCH * 4;
-constexpr int SMEM_BYTES = NSTAGES * STAGE_BYTES + BAR_BYTES + XPOSE_BYTES + 1024;
+template <int BN> constexpr int smem_bytes_res0() { return NSTAGES * TL<BN>::STAGE_BYTES + BAR_BYTES + XPOSE_BYTES + 1024; }
 // RES == 1 (TMA-staged residual epilogue): 5-stage ring, 1 KB of barriers, then 8 warps x 2 buffers of 32 rows x 128 B
 // RES == 2 (fp16 TMA-store epilogue): 5-stage ring, two staging buffers per warp
 constexpr int X_BUF_BYTES = 32 * 128;
@@ -54,10 +58,10 @@ constexpr int X_BUF_BYTES = 32 * 128;
 #define BG_RES1_STAGES 5
 #define BG_RES1_BUFS 2
 #endif
-template <int RES> struct XL {                       // shared-memory layout of the staged-epilogue variants
+template <int RES, int BN> struct XL {               // shared-memory layout of the staged-epilogue variants
   static constexpr int STAGES = RES == 2 ? 5 : BG_RES1_STAGES;
   static constexpr int BUFS = RES == 2 ? 2 : BG_RES1_BUFS;
-  static constexpr int OFF_BAR = STAGES * STAGE_BYTES;
+  static constexpr int OFF_BAR = STAGES * TL<BN>::STAGE_BYTES;
   static constexpr int OFF_STG = OFF_BAR + 1024;
   static constexpr int SMEM_BYTES = OFF_STG + 8 * BUFS * X_BUF_BYTES + 1024;
   static_assert(SMEM_BYTES <= 232448, "staged epilogue does not fit in shared memory");
@@ -75,7 +79,6 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-constexpr int TMEM_COLS = 512;
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;               // shared::cluster address of the same offset in the even (leader) CTA
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -116,13 +119,14 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 
-template <int RES>
+template <int RES, int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p_in,
                  const __grid_constant__ EpiMaps<RES> em) {
   const GemmParams p = gemm_resolve(p_in);
-  constexpr int STAGES = RES ? XL<RES>::STAGES : NSTAGES;
-  constexpr int X_BUFS = XL<RES>::BUFS, X_OFF_BAR = XL<RES>::OFF_BAR, X_OFF_STG = XL<RES>::OFF_STG;
+  constexpr int STAGE_BYTES = TL<BN>::STAGE_BYTES, TMEM_COLS = TL<BN>::TMEM_COLS;
+  constexpr int STAGES = RES ? XL<RES, BN>::STAGES : NSTAGES;
+  constexpr int X_BUFS = XL<RES, BN>::BUFS, X_OFF_BAR = XL<RES, BN>::OFF_BAR, X_OFF_STG = XL<RES, BN>::OFF_STG;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -353,28 +357,33 @@ gemm2_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
 }
 
-}  // namespace
-
-// N % 256 == 0 path of launch_gemm_f16
-int launch_gemm2_f16(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p) {
+// CTA-pair path of launch_gemm_f16: 256-wide column tiles when N % 256 == 0, else 128-wide
+template <int BN>
+int launch_gemm2_bn(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p) {
   const int num_tiles = ((p.M + 255) / 256) * (p.N / BN);
   const int max_clusters = num_sms() / 2;
   const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
   if (!p.out_f16 && p.resid != nullptr && p.resid == p.out && p.ldr == p.ldo && p.rowvec == nullptr) {
-    BG_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&gemm2_f16_kernel<1>), XL<1>::SMEM_BYTES));
+    BG_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&gemm2_f16_kernel<1, BN>), XL<1, BN>::SMEM_BYTES));
     EpiMaps<1> em;
     BG_TRY(make_tmap_2d_f32(&em.x, p.out, (uint64_t)p.M, (uint64_t)p.N, (uint64_t)p.ldo, 32, 32));
-    gemm2_f16_kernel<1><<<2 * clusters, 384, XL<1>::SMEM_BYTES, st>>>(tmA, tmB, p, em);
+    gemm2_f16_kernel<1, BN><<<2 * clusters, 384, XL<1, BN>::SMEM_BYTES, st>>>(tmA, tmB, p, em);
   } else if (p.out_f16 && p.ldo % 8 == 0) {
-    BG_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&gemm2_f16_kernel<2>), XL<2>::SMEM_BYTES));
+    BG_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&gemm2_f16_kernel<2, BN>), XL<2, BN>::SMEM_BYTES));
     EpiMaps<2> em;
     BG_TRY(make_tmap_2d_f16(&em.x, p.out, (uint64_t)p.M, (uint64_t)p.N, (uint64_t)p.ldo, 32, 64));
-    gemm2_f16_kernel<2><<<2 * clusters, 384, XL<2>::SMEM_BYTES, st>>>(tmA, tmB, p, em);
+    gemm2_f16_kernel<2, BN><<<2 * clusters, 384, XL<2, BN>::SMEM_BYTES, st>>>(tmA, tmB, p, em);
   } else {
-    BG_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&gemm2_f16_kernel<0>), SMEM_BYTES));
-    gemm2_f16_kernel<0><<<2 * clusters, 384, SMEM_BYTES, st>>>(tmA, tmB, p, EpiMaps<0>{});
+    BG_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&gemm2_f16_kernel<0, BN>), smem_bytes_res0<BN>()));
+    gemm2_f16_kernel<0, BN><<<2 * clusters, 384, smem_bytes_res0<BN>(), st>>>(tmA, tmB, p, EpiMaps<0>{});
   }
   return check_launch("gemm2_f16_kernel launch");
+}
+
+}  // namespace
+
+int launch_gemm2_f16(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p) {
+  return p.N % 256 == 0 ? launch_gemm2_bn<256>(st, tmA, tmB, p) : launch_gemm2_bn<128>(st, tmA, tmB, p);
 }
 
 }  // namespace bg

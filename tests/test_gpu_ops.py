@@ -44,6 +44,10 @@ GEMM_CASES = [
     (384, 768, 2304, 0, 0, True, False, 3),
     (128 * 170, 2304, 768, 1, 0, True, False, 0),   # 1530 tiles > 148 CTAs: ring + accumulator phases wrap
     (128 * 170 + 5, 768, 1024, 0, 0, True, True, 0),
+    # N % 256 != 0 with many tiles: the CTA-pair kernel with 256 x 128 tiles (all three epilogues)
+    (128 * 300, 128, 1152, 0, 0, True, False, 0),
+    (128 * 300 + 7, 128, 576, 0, 0, True, True, 0),
+    (128 * 300, 384, 256, 1, 1, True, False, 0),
 ]
 
 
