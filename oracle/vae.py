@@ -5,8 +5,10 @@ without conv_shortcut), `_attn2d` and `_upsample2d` reproduce the expected outpu
 tests/models/test_layers_utils.py (ResnetBlock2DTests.test_resnet_default / test_restnet_with_use_in_shortcut,
 AttentionBlockTests.test_attention_block_default, Upsample2DBlockTests.test_upsample_default / test_upsample_with_conv) to 4
 decimals, and the block wiring (resnet -> upsample; resnet -> attention -> resnet) those of test_unet_2d_blocks.py
-(UpDecoderBlock2DTests / UNetMidBlock2DTests).  1-D leaves (ResConvBlock, SelfAttention1d, Upsample1d; diffusers has no known-answer test for them) and the 2-D
-encoder's Downsample2D remain PARITY UNPINNED.  The arithmetic lives in diffusers==0.27 (requirements.txt:5 of the reference), which is absent from
+(UpDecoderBlock2DTests / UNetMidBlock2DTests); the encoder's stride-2 convolution and resnet -> downsample wiring those of
+Downsample2DBlockTests.test_downsample_with_conv / DownEncoderBlock2DTests (with diffusers' default symmetric padding; the
+asymmetric padding=0 variant the VAE uses differs by the one F.pad line).  1-D leaves (ResConvBlock, SelfAttention1d, Upsample1d / Downsample1d; diffusers has no known-answer test for them)
+remain PARITY UNPINNED.  The arithmetic lives in diffusers==0.27 (requirements.txt:5 of the reference), which is absent from
 /root/reference and from this image: `Decoder`, `UNetMidBlock2D`, `UpDecoderBlock2D`, `ResnetBlock2D`, `Attention`,
 `Upsample2D` (surface) and `ResConvBlock`, `SelfAttention1d`, `Upsample1d` (edge).  This file restates their published
 structure around the reference's own wrappers
@@ -20,7 +22,7 @@ Partly pinned since: the EDGE decoder's wrapper -- everything the reference itse
 Decoder1D, UNetMidBlock1D, UpBlock1D: block order and counts, channel wiring, head count, norms, key names) -- is checked
 against outputs of those classes (tests/golden/vae1d_golden.npz, made by tests/golden/make_golden_vae1d.py from the real
 network.py over module forms of the diffusers leaves), and the EDGE encoder's wrapper (AutoencoderKL1DFastEncode,
-Encoder1D) the same way.  The arithmetic inside the diffusers leaves and the whole 2-D decoder / encoder remain unpinned.
+Encoder1D) the same way.  The arithmetic inside the 1-D diffusers leaves remains unpinned.
 """
 from __future__ import annotations
 
@@ -65,6 +67,15 @@ def _attn2d(sd: SD, name: str, x, n_head: int = 1):
     a = a.transpose(1, 2).reshape(N, H * W, C)
     a = a @ sd[name + ".to_out.0.weight"].t() + sd[name + ".to_out.0.bias"]
     return x + a.transpose(1, 2).reshape(N, C, H, W)
+
+
+def _downsample2d(sd: SD, name: str, x, padding: int = 0):
+    """diffusers Downsample2D(use_conv=True): 3x3 convolution with stride 2.  The VAE encoder builds it with padding=0, for
+    which diffusers pads the right / bottom edge by one zero pixel first; padding=1 (diffusers' default, symmetric) exists
+    for diffusers' own known-answer tests."""
+    if padding == 0:
+        x = F.pad(x, (0, 1, 0, 1), mode="constant", value=0)
+    return F.conv2d(x, sd[name + ".conv.weight"], sd[name + ".conv.bias"], stride=2, padding=padding)
 
 
 def _upsample2d(sd: SD, name: str, x):
@@ -141,7 +152,8 @@ def edge_decode(sd: SD, z: torch.Tensor) -> torch.Tensor:
 
 # ------------------------------------------------------------------------------------------------ encoders (config 1)
 # AutoencoderKLFastEncode.forward network.py:927-945 and AutoencoderKL1DFastEncode.forward :745-783 return
-# DiagonalGaussianDistribution(quant_conv(encoder(x))).mode() = the first half of the channels.  PARITY UNPINNED (diffusers).
+# DiagonalGaussianDistribution(quant_conv(encoder(x))).mode() = the first half of the channels (2-D leaves pinned by
+# tests/test_oracle_vae_kat.py; 1-D leaves unpinned).
 def surf_encode(sd: SD, x: torch.Tensor) -> torch.Tensor:
     """x (N,3,H,W), H and W divisible by 8 -> latent mode (N,3,H/8,W/8)"""
     e = "encoder"
@@ -149,10 +161,8 @@ def surf_encode(sd: SD, x: torch.Tensor) -> torch.Tensor:
     for i in range(4):
         for j in range(2):
             h = _resnet2d(sd, f"{e}.down_blocks.{i}.resnets.{j}", h)
-        if i < 3:   # diffusers Downsample2D(padding=0): pad right/bottom by one, 3x3 stride 2
-            h = F.pad(h, (0, 1, 0, 1), mode="constant", value=0)
-            h = F.conv2d(h, sd[f"{e}.down_blocks.{i}.downsamplers.0.conv.weight"],
-                         sd[f"{e}.down_blocks.{i}.downsamplers.0.conv.bias"], stride=2)
+        if i < 3:
+            h = _downsample2d(sd, f"{e}.down_blocks.{i}.downsamplers.0", h, padding=0)
     h = _resnet2d(sd, f"{e}.mid_block.resnets.0", h)
     h = _attn2d(sd, f"{e}.mid_block.attentions.0", h)
     h = _resnet2d(sd, f"{e}.mid_block.resnets.1", h)

@@ -93,3 +93,24 @@ def test_unet_mid_block():                # UNetMidBlock2DTests.test_output: res
         y = V._attn2d(sd, "a", y, n_head=32)
         y = V._resnet2d(sd, "r1", y, temb_add=r1[1](silu(temb))[:, :, None, None])
     _check(y, [-0.1062, 1.7248, 0.3494, 1.4569, -0.0910, -1.2421, -0.9984, 0.6736, 1.0028])
+
+
+def test_downsample_with_conv():          # Downsample2DBlockTests.test_downsample_with_conv (default padding = 1)
+    torch.manual_seed(0)
+    sample = torch.randn(1, 32, 64, 64)
+    sd = _conv("d.conv", nn.Conv2d(32, 32, 3, stride=2, padding=1))
+    with torch.no_grad():
+        out = V._downsample2d(sd, "d", sample, padding=1)
+    assert out.shape == (1, 32, 32, 32)
+    _check(out, [0.9267, 0.5878, 0.3337, 1.2321, -0.1191, -0.3984, -0.7532, -0.0715, -0.3913])
+
+
+def test_down_encoder_block():            # DownEncoderBlock2DTests.test_output: ResnetBlock2D (no time embedding) -> Downsample2D
+    torch.manual_seed(0)
+    x = torch.randn(4, 32, 32, 32)
+    c1, c2, d = nn.Conv2d(32, 32, 3, padding=1), nn.Conv2d(32, 32, 3, padding=1), nn.Conv2d(32, 32, 3, stride=2, padding=1)
+    sd = {**_gn("r.norm1", 32), **_gn("r.norm2", 32), **_conv("r.conv1", c1), **_conv("r.conv2", c2), **_conv("d.conv", d)}
+    with torch.no_grad():
+        out = V._downsample2d(sd, "d", V._resnet2d(sd, "r", x), padding=1)
+    assert out.shape == (4, 32, 16, 16)
+    _check(out, [1.1102, 0.5302, 0.4872, -0.0023, -0.8042, 0.0483, -0.3489, -0.5632, 0.7626])
