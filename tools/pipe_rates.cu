@@ -14,7 +14,7 @@ constexpr int ITER = 2000;
 constexpr int UNROLL = 16;
 
 enum Op { FFMA, FFMA2_RRR, FFMA2, FADD2, FMUL2, FMNMX3, F2FP, MUFU, MUFU_FFMA2_1_4, MUFU_FFMA_1_8, FFMA2_F2FP, FFMA2_FMNMX3,
-          MUFU_H2, ADD_F32_F16, MUFU_3OTHER, MUFU_7OTHER, MUFU_H2_7OTHER, HADD2, FMNMX };
+          MUFU_H2, ADD_F32_F16, MUFU_3OTHER, MUFU_7OTHER, MUFU_H2_7OTHER, HADD2, FMNMX, MUFU_F2FP, MUFU_2F2FP };
 
 template <int OP>
 __global__ void rate_kernel(float* out, long long* cycles, float seed) {
@@ -91,6 +91,15 @@ __global__ void rate_kernel(float* out, long long* cycles, float seed) {
         constexpr int NO = OP == MUFU_3OTHER ? 3 : 7;
 #pragma unroll
         for (int k = 0; k < NO; ++k) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(y[(i + k) % UNROLL]) : "f"(a), "f"(b));
+      } else if (OP == MUFU_F2FP || OP == MUFU_2F2FP) {   // do MUFU.EX2 and F2FP share a pipe?  (8 + 4 = 12 if they do, 8 if not)
+        asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x[i]));
+        unsigned h;
+        asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(y[i]), "f"(y[(i + 1) % UNROLL]));
+        y[i] = __uint_as_float(h & 0x3fffffffu);
+        if (OP == MUFU_2F2FP) {
+          asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(y[(i + 2) % UNROLL]), "f"(y[(i + 3) % UNROLL]));
+          y[(i + 2) % UNROLL] = __uint_as_float(h & 0x3fffffffu);
+        }
       } else if (OP == MUFU_FFMA2_1_4) {      // the attention pattern: 1 MUFU per 4 packed FMA-pipe instructions
         if ((i & 3) == 0) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x[i]));
         asm volatile(
@@ -167,6 +176,8 @@ int main() {
   run<ADD_F32_F16>("add.rn.f32.f16 (mixed)", 1);
   run<HADD2>("HADD2", 1);
   printf("mixed (cycles per unroll step = the group in the name):\n");
+  run<MUFU_F2FP>("1 MUFU + 1 F2FP per step", 1);
+  run<MUFU_2F2FP>("1 MUFU + 2 F2FP per step", 1);
   run<MUFU_3OTHER>("1 MUFU + 3 FFMA per step", 1);
   run<MUFU_7OTHER>("1 MUFU + 7 FFMA per step", 1);
   run<MUFU_H2_7OTHER>("1 MUFU.F16x2 + 7 FFMA per step", 1);
