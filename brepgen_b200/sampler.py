@@ -46,6 +46,51 @@ class CascadeConfig:
                                          # graph and replay it; auto = on for launch-bound shapes (few tokens, many steps)
 
 
+def config_from_eval_args(eval_args: dict, **overrides) -> CascadeConfig:
+    """One entry of the reference's eval_config.yaml (`config[mode]`, sample.py:379-381) -> CascadeConfig, as sample()
+    reads it (sample.py:39-51): batch_size, bbox_threshold, num_surfaces, num_edges, use_cf and, for classifier-free runs, the
+    class label looked up in text2int (sample.py:21-32; an unknown label raises KeyError like the reference).  z_threshold
+    and save_folder belong to the post-processing half (sample.py:303-368) and are ignored here."""
+    use_cf = bool(eval_args["use_cf"])
+    cfg = CascadeConfig(batch_size=int(eval_args["batch_size"]), num_surfaces=int(eval_args["num_surfaces"]),
+                        num_edges=int(eval_args["num_edges"]), use_cf=use_cf,
+                        class_label=TEXT2INT[eval_args["class_label"]] if use_cf else 0,
+                        bbox_threshold=float(eval_args["bbox_threshold"]))
+    for k, v in overrides.items():
+        if not hasattr(cfg, k):
+            raise TypeError(f"CascadeConfig has no field {k!r}")
+        setattr(cfg, k, v)
+    return cfg
+
+
+def load_cascade(eval_args: dict, device="cuda", load=torch.load) -> "Cascade":
+    """The model-loading block of sample() (sample.py:56-99): the four denoisers from `*_weight` checkpoints of state dicts
+    (strict), the two decoders from the full-autoencoder checkpoints (strict=False: `encoder.*` / `quant_conv.*` are ignored),
+    constructed with the reference's keyword arguments, moved to `device`, eval()."""
+    from .models import EdgePosNet, EdgeZNet, SurfPosNet, SurfZNet
+    from .vae import AutoencoderKL1DFastDecode, AutoencoderKLFastDecode
+    use_cf = bool(eval_args["use_cf"])
+    models = {}
+    for name, cls, key in (("surfpos", SurfPosNet, "surfpos_weight"), ("surfz", SurfZNet, "surfz_weight"),
+                           ("edgepos", EdgePosNet, "edgepos_weight"), ("edgez", EdgeZNet, "edgez_weight")):
+        m = cls(use_cf)
+        m.load_state_dict(load(eval_args[key]))
+        models[name] = m.to(device).eval()
+    surf_vae = AutoencoderKLFastDecode(
+        in_channels=3, out_channels=3,
+        down_block_types=["DownEncoderBlock2D", "DownEncoderBlock2D", "DownEncoderBlock2D", "DownEncoderBlock2D"],
+        up_block_types=["UpDecoderBlock2D", "UpDecoderBlock2D", "UpDecoderBlock2D", "UpDecoderBlock2D"],
+        block_out_channels=[128, 256, 512, 512], layers_per_block=2, act_fn="silu", latent_channels=3, norm_num_groups=32,
+        sample_size=512)
+    surf_vae.load_state_dict(load(eval_args["surfvae_weight"]), strict=False)
+    edge_vae = AutoencoderKL1DFastDecode(
+        in_channels=3, out_channels=3, down_block_types=["DownBlock1D", "DownBlock1D", "DownBlock1D"],
+        up_block_types=["UpBlock1D", "UpBlock1D", "UpBlock1D"], block_out_channels=[128, 256, 512], layers_per_block=2,
+        act_fn="silu", latent_channels=3, norm_num_groups=32, sample_size=512)
+    edge_vae.load_state_dict(load(eval_args["edgevae_weight"]), strict=False)
+    return Cascade(models, surf_vae.to(device).eval(), edge_vae.to(device).eval(), device=device)
+
+
 def shard_batch(global_batch: int, rank: int, world_size: int):
     """contiguous shard [lo, hi) of the batch owned by `rank` (sizes differ by at most one)"""
     base, rem = divmod(global_batch, world_size)

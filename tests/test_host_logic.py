@@ -234,3 +234,47 @@ def test_reference_loader_runs_the_reference_classes_when_available():
     with torch.no_grad():
         y = m(torch.zeros(1, 4, 6), torch.tensor([3]), None)
     assert y.shape == (1, 4, 6)
+
+
+def test_load_cascade_and_config_from_eval_args():
+    """sample.py:39-99: eval_config.yaml entry -> CascadeConfig, and the six checkpoints -> drop-in modules (CPU: the modules
+    only hold parameters until their first CUDA forward).  The VAE checkpoints are full autoencoders: extra keys are ignored."""
+    from brepgen_b200.sampler import TEXT2INT, config_from_eval_args, load_cascade
+    from brepgen_b200.spec import denoiser_spec, edge_decoder_spec, surf_decoder_spec
+    from brepgen_b200.synth import synth_state_dict
+    args = {"save_folder": "x", "batch_size": 16, "z_threshold": 0.2, "bbox_threshold": 0.08, "num_surfaces": 60,
+            "num_edges": 40, "use_cf": True, "class_label": "chair"}
+    sds, store = {}, {}                  # `store` stands in for torch.load(path): no gigabytes written in a unit test
+    for i, kind in enumerate(("surfpos", "surfz", "edgepos", "edgez")):
+        sds[kind] = synth_state_dict(denoiser_spec(kind, True), seed=40 + i)
+        args[f"{kind}_weight"] = f"{kind}.pt"
+        store[args[f"{kind}_weight"]] = sds[kind]
+    for name, spec, seed in (("surfvae", surf_decoder_spec(), 50), ("edgevae", edge_decoder_spec(), 51)):
+        sds[name] = synth_state_dict(spec, seed=seed)
+        full = {**sds[name], "encoder.conv_in.weight": torch.zeros(4, 3, 3), "quant_conv.weight": torch.zeros(6, 6, 1)}
+        args[f"{name}_weight"] = f"{name}.pt"
+        store[args[f"{name}_weight"]] = full
+
+    cfg = config_from_eval_args(args, schedule="ddpm", ddpm_steps=4)
+    assert (cfg.batch_size, cfg.num_surfaces, cfg.num_edges, cfg.use_cf, cfg.class_label) == (16, 60, 40, True, TEXT2INT["chair"])
+    assert cfg.bbox_threshold == 0.08 and cfg.schedule == "ddpm" and cfg.ddpm_steps == 4
+    with pytest.raises(KeyError):
+        config_from_eval_args({**args, "class_label": "spaceship"})
+    with pytest.raises(TypeError):
+        config_from_eval_args(args, no_such_field=1)
+    assert config_from_eval_args({**args, "use_cf": False, "class_label": []}).class_label == 0
+
+    casc = load_cascade(args, device="cpu", load=store.__getitem__)
+    for kind in ("surfpos", "surfz", "edgepos", "edgez"):
+        got = casc.m[kind].state_dict()
+        assert set(got) == set(sds[kind]) and all(torch.equal(got[k], sds[kind][k]) for k in got)
+        assert not casc.m[kind].training
+    for mod, name in ((casc.surf_vae, "surfvae"), (casc.edge_vae, "edgevae")):
+        got = mod.state_dict()
+        assert all(torch.equal(got[k], sds[name][k]) for k in sds[name] if k in got) and "encoder.conv_in.weight" not in got
+    # a denoiser checkpoint with a missing key is an error (strict load, like the reference)
+    bad = dict(sds["surfpos"])
+    bad.pop(next(iter(bad)))
+    store[args["surfpos_weight"]] = bad
+    with pytest.raises(RuntimeError):
+        load_cascade(args, device="cpu", load=store.__getitem__)
