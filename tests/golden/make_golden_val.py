@@ -65,26 +65,37 @@ def oracle_callables(sd):
     return models, (lambda x: V.surf_encode(sd["surf_enc"], x)), (lambda x: V.edge_encode(sd["edge_enc"], x))
 
 
+CF_LABEL = torch.tensor([[6], [3]])      # (B, 1) int64 class labels of the classifier-free case ('chair', 'bench')
+
+
+def state_dicts_cf():
+    """the classifier-free variants of the four denoisers (class embedding table); encoders as in state_dicts()"""
+    sd = state_dicts()
+    for i, kind in enumerate(("surfpos", "surfz", "edgepos", "edgez")):
+        sd[kind] = synth_state_dict(denoiser_spec(kind, True), seed=60 + i)
+    return sd
+
+
 def main():
     src = open(REF).read().splitlines()
-    sd = state_dicts()
-    models, surf_vae, edge_vae = oracle_callables(sd)
     inp = inputs()
     sched = DDPMOracle()
     sched.config = SimpleNamespace(num_train_timesteps=1000)
     out = {k: v.numpy() for k, v in inp.items()}
-    for name, (a, b) in BLOCKS.items():
-        body = textwrap.dedent("\n".join(src[a - 1:b]))
-        nsteps = 5 if name in ("surfpos", "surfz") else 3
-        ns = dict(torch=torch, nn=nn, mse_loss=nn.MSELoss(reduction="none"), total_loss=[0] * nsteps, total_count=0,
-                  bsz=B, class_label=None,
-                  self=SimpleNamespace(model=models[name], surf_vae=surf_vae, edge_vae=edge_vae, noise_scheduler=sched,
-                                       device="cpu", z_scaled=Z_SCALED, max_edge=E),
-                  **{k: v.clone() for k, v in inp.items()})
-        torch.manual_seed(SEEDS[name])
-        exec(compile(body, f"trainer.py:{a}-{b}", "exec"), ns)
-        out[f"loss_{name}"] = np.asarray(ns["total_loss"], dtype=np.float64)
-        print(name, ns["total_loss"])
+    for tag, sd, label in (("", state_dicts(), None), ("_cf", state_dicts_cf(), CF_LABEL)):
+        models, surf_vae, edge_vae = oracle_callables(sd)
+        for name, (a, b) in BLOCKS.items():
+            body = textwrap.dedent("\n".join(src[a - 1:b]))
+            nsteps = 5 if name in ("surfpos", "surfz") else 3
+            ns = dict(torch=torch, nn=nn, mse_loss=nn.MSELoss(reduction="none"), total_loss=[0] * nsteps, total_count=0,
+                      bsz=B, class_label=None if label is None else label.clone(),
+                      self=SimpleNamespace(model=models[name], surf_vae=surf_vae, edge_vae=edge_vae, noise_scheduler=sched,
+                                           device="cpu", z_scaled=Z_SCALED, max_edge=E),
+                      **{k: v.clone() for k, v in inp.items()})
+            torch.manual_seed(SEEDS[name])
+            exec(compile(body, f"trainer.py:{a}-{b}", "exec"), ns)
+            out[f"loss_{name}{tag}"] = np.asarray(ns["total_loss"], dtype=np.float64)
+            print(name + tag, ns["total_loss"])
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "val_golden.npz"), **out)
 
 

@@ -10,7 +10,7 @@ import pytest
 import torch
 
 from brepgen_b200 import validation as VAL
-from make_golden_val import SEEDS, Z_SCALED, oracle_callables, state_dicts
+from make_golden_val import CF_LABEL, SEEDS, Z_SCALED, oracle_callables, state_dicts, state_dicts_cf
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "val_golden.npz")
 
@@ -21,29 +21,31 @@ def _load(device="cpu"):
     return g, t
 
 
-def _run_all(models, surf_vae, edge_vae, sched, t):
+def _run_all(models, surf_vae, edge_vae, sched, t, label=None):
     out = {}
+    lab = (lambda: None) if label is None else (lambda: label.clone())   # the reference may modify labels in place (is_train)
     torch.manual_seed(SEEDS["surfpos"])
-    out["surfpos"] = VAL.surfpos_val_losses(models["surfpos"], sched, t["surfPos"], None, rng_device="cpu")
+    out["surfpos"] = VAL.surfpos_val_losses(models["surfpos"], sched, t["surfPos"], lab(), rng_device="cpu")
     torch.manual_seed(SEEDS["surfz"])
-    out["surfz"] = VAL.surfz_val_losses(models["surfz"], surf_vae, sched, t["surfPos"], t["surfPnt"], t["surf_mask"], None, Z_SCALED,
+    out["surfz"] = VAL.surfz_val_losses(models["surfz"], surf_vae, sched, t["surfPos"], t["surfPnt"], t["surf_mask"], lab(), Z_SCALED,
                                         rng_device="cpu")
     torch.manual_seed(SEEDS["edgepos"])
     out["edgepos"] = VAL.edgepos_val_losses(models["edgepos"], surf_vae, sched, t["edgePos"], t["surfPnt"], t["surfPos"],
-                                            t["surf_mask"], None, Z_SCALED, rng_device="cpu")
+                                            t["surf_mask"], lab(), Z_SCALED, rng_device="cpu")
     torch.manual_seed(SEEDS["edgez"])
     out["edgez"] = VAL.edgez_val_losses(models["edgez"], surf_vae, edge_vae, sched, t["edgePnt"], t["edgePos"], t["edge_mask"],
-                                        t["surfPnt"], t["surfPos"], t["vertPos"], None, Z_SCALED, rng_device="cpu")
+                                        t["surfPnt"], t["surfPos"], t["vertPos"], lab(), Z_SCALED, rng_device="cpu")
     return out
 
 
-def test_validation_glue_matches_reference_statements():
+@pytest.mark.parametrize("cf", [False, True])
+def test_validation_glue_matches_reference_statements(cf):
     from oracle.schedulers import DDPMOracle
     g, t = _load()
-    models, surf_vae, edge_vae = oracle_callables(state_dicts())
-    out = _run_all(models, surf_vae, edge_vae, DDPMOracle(), t)
+    models, surf_vae, edge_vae = oracle_callables(state_dicts_cf() if cf else state_dicts())
+    out = _run_all(models, surf_vae, edge_vae, DDPMOracle(), t, CF_LABEL if cf else None)
     for name, got in out.items():
-        ref = g[f"loss_{name}"]
+        ref = g[f"loss_{name}_cf" if cf else f"loss_{name}"]
         assert len(got) == len(ref)
         assert np.allclose(np.asarray(got), ref, rtol=1e-5, atol=0), (name, got, ref)
 
